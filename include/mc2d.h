@@ -1,0 +1,217 @@
+/*
+ * mc2d.h — C ABI of libmc2d.so, the B200 (sm_100a) implementation of the 2D Monte Carlo hot
+ * path of ReyhanehFarimani/MonteCarlo_simulation.
+ *
+ * The reference has no FFI layer: its boundary is the C++ class API of serial_src/ and mpi_src/
+ * linked into one binary.  This header is what those classes bind to when the
+ * hot path runs on the GPU; montecarlo_simulation_b200/host/ holds the C++ shims that keep the
+ * reference's class names and signatures and forward to these entry points.  Each entry point
+ * cites the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an mc2d_status and never
+ * throws; all buffers are caller-owned HOST memory unless a name ends in _dev; one context per
+ * GPU; calls on one context are serialised by the caller (the reference is single-threaded per
+ * rank, SURVEY.md §8b "Threading").  Positions are packed {double x, y} — exactly the layout of
+ * serial_src/initial.h:10-27 `Particle`, so `particles.data()` can be passed as is.
+ */
+#ifndef MC2D_H
+#define MC2D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC2D_ABI_VERSION 1
+
+typedef enum {
+    MC2D_OK = 0,
+    MC2D_ERR_INVALID = 1,       /* bad argument (reference: std::invalid_argument / assert) */
+    MC2D_ERR_CUDA = 2,          /* CUDA runtime failure; see mc2d_last_error */
+    MC2D_ERR_NO_DEVICE = 3,     /* no CUDA device: there is NO CPU fallback */
+    MC2D_ERR_CELL_OVERFLOW = 4, /* a cell needs more than cell_capacity slots */
+    MC2D_ERR_GEOMETRY = 5,      /* box too small for the checkerboard (needs >= 2 cells of side >= rcut per direction, even counts per slab) */
+    MC2D_ERR_OUT_OF_BOX = 6,    /* a position is NaN or outside [0,Lx] x [0,Ly] */
+    MC2D_ERR_NCCL = 7,
+    MC2D_ERR_STATE = 8          /* call out of order (e.g. sweep before upload) */
+} mc2d_status;
+
+/* PotentialType, in the order of serial_src/potential.h:11-18 */
+typedef enum {
+    MC2D_LENNARD_JONES = 0,
+    MC2D_WCA = 1,
+    MC2D_YUKAWA = 2,
+    MC2D_ATHERMAL_STAR = 3,
+    MC2D_THERMAL_STAR = 4,
+    MC2D_IDEAL = 5
+} mc2d_potential;
+
+/* Everything the reference spreads over SimulationBox (initial.h:31-38), ThermodynamicCalculator
+ * (thermodynamic_calculator.h:186-199) and MonteCarlo (MC.h:76-94). */
+typedef struct {
+    double Lx, Ly;  /* periodic box */
+    double rcut;    /* interaction cutoff; cells have side >= rcut */
+    int potential;  /* mc2d_potential */
+    /* shape parameters ALREADY derived as thermodynamic_calculator.cpp:19-21 does
+     * (f' = (2+9f^2)/24, f_d' = A0 f^2/kappa) and narrowed to float as potential.h:151 does */
+    float f_prime, f_d_prime, kappa, alpha;
+    double temperature;
+    double activity;  /* z; the reference reads it from the input key "mu" (MC.cpp:25) */
+    double delta;     /* max displacement per coordinate (MC.cpp:100-101) */
+    uint64_t seed;    /* Philox key; one counter-based stream per cell */
+    int device;       /* CUDA device ordinal */
+    int rank, nranks; /* 1-D slab decomposition in x (replaces mpi_src Decomposition Px x Py) */
+    int cell_capacity; /* particle slots per cell; 0 = choose from rcut and a dense-packing bound */
+    double p_insert, p_delete; /* per GC draw (MC.cpp:194-215: 0.3 / 0.3, rest no-op); 0,0 = those defaults */
+} mc2d_params;
+
+typedef struct {
+    long long attempted[3]; /* displacement, insertion, deletion trials (no-ops are not counted) */
+    long long accepted[3];
+    long long n_particles;  /* owned by this rank */
+    double energy;          /* running potential energy of this rank's moves + its share at the last resync */
+    long long overflow;     /* insertions refused because the cell had no free slot (should be 0) */
+    unsigned long long sweeps_done;
+} mc2d_stats;
+
+/* what one sweep does.  One sweep = 4 colour passes; in each pass every cell of that colour gets
+ * disp_per_particle * n_cell displacement trials (MC.cpp:38-44: N trials per sweep) followed by
+ * gc_per_cell grand-canonical draws (MC.cpp:45-52), each an insertion / deletion / no-op. */
+typedef struct {
+    int disp_per_particle; /* 0 disables displacements */
+    int gc_per_cell;       /* 0 = NVT */
+    int shift_grid;        /* 1: random grid shift before every sweep (ergodicity); 0: frozen grid */
+} mc2d_sweep_plan;
+
+typedef struct mc2d_ctx mc2d_ctx;
+
+const char *mc2d_status_string(int status);
+const char *mc2d_last_error(const mc2d_ctx *ctx); /* detail text of the last failure on ctx */
+int mc2d_abi_version(void);
+/* number of visible CUDA devices (0 on a CPU-only host; never an error) */
+int mc2d_device_count(void);
+
+/* -- lifetime (MonteCarlo ctor MC.cpp:4-29 / dtor) ------------------------------------------- */
+int mc2d_create(const mc2d_params *params, mc2d_ctx **out);
+int mc2d_destroy(mc2d_ctx *ctx);
+
+/* -- pure host geometry (no GPU needed) ------------------------------------------------------ */
+/* CellList ctor, cell_list.cpp:5-15: nx = int(Lx/rcut) (>=1), cell_dx = Lx/nx */
+int mc2d_reference_grid(double Lx, double Ly, double rcut, int *nx, int *ny, double *cell_dx, double *cell_dy);
+/* checkerboard grid: largest nx that is a multiple of 2*nranks with Lx/nx >= rcut (CellListParallel's
+ * even-count rule, cell_list_parallel.cpp:64-106, applied per slab); ny largest even with Ly/ny >= rcut */
+int mc2d_sweep_grid(double Lx, double Ly, double rcut, int nranks, int *nx, int *ny, double *cell_dx,
+                    double *cell_dy);
+/* slab of `rank`: first owned cell column and number of owned columns (replaces
+ * Decomposition::localBounds, simulatin_box.cpp:91-98, for Px = nranks, Py = 1) */
+int mc2d_slab_columns(int nx, int nranks, int rank, int *col0, int *ncol);
+/* which boundary column a colour pass modifies and where it goes: colour = px + 2*py.
+ * *send_left = 1: the rank's first owned column goes to rank-1 (its right ghost); else the last
+ * owned column goes to rank+1.  (replaces the 8-neighbour flushGhostUpdates, particle_exchange.cpp:247-258) */
+int mc2d_halo_route(int colour, int rank, int nranks, int *send_left, int *send_to, int *recv_from);
+/* the colour order and grid shift of sweep `sweep` — a pure function of (seed, sweep), identical on
+ * every rank (replaces bcast_seed_, MC_parallel.cpp:218-230) */
+int mc2d_sweep_schedule(uint64_t seed, uint64_t sweep, double cell_dx, double cell_dy, int shift_grid,
+                        int colour_order[4], double *shift_x, double *shift_y);
+
+/* -- particles --------------------------------------------------------------------------------
+ * upload: takes n packed positions (ids optional, NULL = 0..n-1) and keeps those inside this
+ * rank's slab (all of them when nranks == 1); bins them on the checkerboard grid by a key sort +
+ * cell-offset pass (replaces CellList::build, cell_list.cpp:28-41, and buildInterior,
+ * cell_list_parallel.cpp:116-132) and computes the initial energy (MC.cpp:26). */
+int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long long n);
+/* download: owned particles in cell order; *n_out receives the count (cap = capacity of xy/ids in
+ * particles; MC2D_ERR_INVALID if too small).  ids may be NULL.  Particles inserted by GC moves
+ * carry id -1. */
+int mc2d_download(mc2d_ctx *ctx, double *xy, int *ids, long long cap, long long *n_out);
+int mc2d_num_particles(mc2d_ctx *ctx, long long *n_local);
+
+/* -- the step loop (MonteCarlo::run, MC.cpp:31-78; MonteCarloNVT_MPI::run, MC_parallel.cpp:57-114) */
+int mc2d_run_sweeps(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_plan *plan, mc2d_stats *stats_out);
+int mc2d_get_stats(mc2d_ctx *ctx, mc2d_stats *stats_out);
+int mc2d_reset_counters(mc2d_ctx *ctx);
+int mc2d_set_delta(mc2d_ctx *ctx, double delta);
+int mc2d_set_activity(mc2d_ctx *ctx, double z);
+
+/* full-system energy U, virial W (sum over pairs of r.f) and particle count of the context's
+ * current configuration (computeTotalEnergyCellList / computeTotalVirialCellList,
+ * thermodynamic_calculator.cpp:194-232, in ONE pass).  resync != 0 stores U as the running energy
+ * (MC.cpp:62-71).  Local to this rank unless allreduce != 0 and a communicator is attached
+ * (replaces the MPI_Allreduce sites of thermodynamic_calculator_parallel.cpp:41-131). */
+int mc2d_total_energy_virial(mc2d_ctx *ctx, int resync, int allreduce, double *U, double *W, long long *N);
+
+/* -- ThermodynamicCalculator on caller-owned particle vectors, on the REFERENCE grid
+ * (nx = int(Lx/rcut)), results comparable bit-for-bit / to 1e-10 with the serial reference ---- */
+/* computeTotalEnergyCellList + computeTotalVirialCellList (thermodynamic_calculator.cpp:194-232);
+ * pressure = rho*T + W/(2V) (:235-242) follows on the host. */
+int mc2d_calc_energy_virial(mc2d_ctx *ctx, const double *xy, long long n, double *U, double *W);
+/* CellList::cellIndex for each particle (cell_list.cpp:103-109), bit-exact */
+int mc2d_calc_cell_ids(mc2d_ctx *ctx, const double *xy, long long n, int *cell_out);
+/* getNeighbors(i).size() for each particle (cell_list.cpp:43-70, inclusive cutoff), bit-exact;
+ * local_energy_out (optional) = computeLocalEnergy over that list (thermodynamic_calculator.h:103-121) */
+int mc2d_calc_neighbor_counts(mc2d_ctx *ctx, const double *xy, long long n, int *count_out,
+                              double *local_energy_out);
+/* energy of nq trial points against the configuration: computeLocalEnergy over getNeighbors2(point)
+ * (cell_list.cpp:72-101) skipping particle exclude[q] when >= 0 (exclude may be NULL).  This is
+ * the dE hook: displacement dE = E(new, exclude=i) - E(old_i, exclude=i); insertion dE = E(pt);
+ * deletion dE = -E(old_i, exclude=i).  count_out optional. */
+int mc2d_calc_point_energies(mc2d_ctx *ctx, const double *xy, long long n, const double *points,
+                             const int *exclude, long long nq, double *energy_out, int *count_out);
+
+/* -- trial log (parity hook for per-trial dE of the sweep kernel) ----------------------------------- */
+typedef struct {
+    int pass;        /* 0..3 position of the colour pass inside the sweep */
+    int cell;        /* global cell id (column-major: cx*ny + cy) */
+    int seq;         /* order of the trial inside its cell visit */
+    int kind;        /* 0 displacement, 1 insertion, 2 deletion */
+    int accepted;
+    int reserved;
+    double old_x, old_y; /* displacement/deletion: the particle's position before the trial */
+    double new_x, new_y; /* displacement: trial position (wrapped into the box); insertion: the point */
+    double dE;           /* energy change the kernel used in the acceptance rule (NaN if rejected before evaluation) */
+} mc2d_trial;
+/* runs ONE sweep and records up to cap trials; *n_out = number of trials that happened */
+int mc2d_run_sweep_traced(mc2d_ctx *ctx, const mc2d_sweep_plan *plan, mc2d_trial *trials, long long cap,
+                          long long *n_out, mc2d_stats *stats_out);
+
+/* -- multi-GPU (replaces ParticleExchange, particle_exchange.h:33-51, and the Allreduce sites) ---- */
+#define MC2D_UNIQUE_ID_BYTES 128
+/* rank 0 creates the id, the host program ships it to the other ranks (MPI_Bcast in the reference's
+ * world, torch.distributed in bench.py), then every rank calls mc2d_comm_init. */
+int mc2d_comm_unique_id(void *id_out /* MC2D_UNIQUE_ID_BYTES */);
+int mc2d_comm_init(mc2d_ctx *ctx, const void *unique_id);
+/* sums stats over ranks (one ncclAllReduce of a small double vector) */
+int mc2d_allreduce_stats(mc2d_ctx *ctx, mc2d_stats *inout);
+
+/* -- introspection for benchmarks ------------------------------------------------------------ */
+typedef struct {
+    int nx, ny;            /* checkerboard grid */
+    int col0, ncol;        /* owned columns */
+    int cell_capacity;
+    double cell_dx, cell_dy;
+    long long launches;    /* kernels launched by this context so far */
+    double last_sweep_ms;  /* device time of the last mc2d_run_sweeps call (CUDA events) */
+    double last_energy_ms; /* device time of the last energy/virial reduction */
+    long long last_pair_tests; /* directed distance tests of the last energy/virial reduction */
+    long long last_pair_evals; /* directed in-cutoff pair evaluations of the last reduction */
+    /* per-kernel device time of the last mc2d_run_sweeps call made with kernel timing on
+     * (CUDA events around every launch on the context's stream) */
+    double k_sweep_ms;
+    long long k_sweep_launches;
+    double k_rebin_ms;
+    long long k_rebin_launches;
+} mc2d_info;
+int mc2d_get_info(mc2d_ctx *ctx, mc2d_info *out);
+/* on != 0: bracket every sweep / re-bin kernel with CUDA events (adds launch gaps: use it for the
+ * roofline measurement, not for the throughput number) */
+int mc2d_set_kernel_timing(mc2d_ctx *ctx, int on);
+/* raw CUDA stream (cudaStream_t) the context launches on, for callers that time with events */
+int mc2d_get_stream(mc2d_ctx *ctx, void **stream_out);
+int mc2d_synchronize(mc2d_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MC2D_H */

@@ -1,0 +1,1144 @@
+// mc2d.cu — host side of libmc2d.so: context, launch logic and the C ABI of include/mc2d.h.
+// The kernels are in mc2d_kernels.cuh.  There is NO CPU fallback: without a CUDA device every
+// compute entry point fails with MC2D_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cub/cub.cuh>
+#include <string>
+#include <vector>
+
+#include "mc2d_kernels.cuh"
+
+#if __has_include(<nccl.h>)
+#include <nccl.h>
+#define MC2D_HAVE_NCCL_H 1
+#else
+#define MC2D_HAVE_NCCL_H 0
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+#if MC2D_HAVE_NCCL_H
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) =
+        nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string &err) {
+        if (handle) return true;
+        // RTLD_NOLOAD first: reuse the NCCL a host program (e.g. torch) already loaded
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!handle) handle = dlopen("libnccl.so.2", RTLD_NOW);
+        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW);
+        if (!handle) {
+            err = std::string("cannot load libnccl: ") + dlerror();
+            return false;
+        }
+#define MC2D_SYM(name)                                                        \
+    name = reinterpret_cast<decltype(name)>(dlsym(handle, "nccl" #name));     \
+    if (!name) {                                                              \
+        err = "libnccl lacks nccl" #name;                                     \
+        return false;                                                         \
+    }
+        MC2D_SYM(GetUniqueId) MC2D_SYM(CommInitRank) MC2D_SYM(CommDestroy) MC2D_SYM(Send) MC2D_SYM(Recv)
+        MC2D_SYM(GroupStart) MC2D_SYM(GroupEnd) MC2D_SYM(AllReduce) MC2D_SYM(GetErrorString)
+#undef MC2D_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+#endif
+
+inline int even_up(int v, int m) { return ((v + m - 1) / m) * m; }
+
+}  // namespace
+
+struct mc2d_ctx {
+    mc2d_params prm;
+    PairParams pp;
+    double r2cut = 0, beta = 0;
+    double p_ins = 0.3, p_del = 0.3;
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+
+    Grid g{};
+    bool have_particles = false;
+    bool sweep_ok = true;  // false: box too small for the checkerboard, calculator hooks only
+    bool use_ids = false;
+    int cur = 0;
+    double2 *pos[2] = {nullptr, nullptr};
+    int *cnt[2] = {nullptr, nullptr};
+    int *ids[2] = {nullptr, nullptr};
+    int allocK = 0;
+
+    unsigned long long *d_counters = nullptr;  // 8
+    double *d_energy = nullptr;                // [0] running, [1] U, [2] W, [3] N
+    unsigned long long *d_pair_stats = nullptr;  // 2 + [2] particle count
+    int *d_err = nullptr;                      // [0] overflow need, [1] flags, [2] max count
+    DevBuf partial, trace_buf;
+    DevBuf xy_in, ids_in, keys, keys_sorted, idx, idx_sorted, spos, sids, start, cub_tmp, pts, excl, outE, outC,
+        outI, offsets;
+    unsigned long long *d_trace_n = nullptr;
+
+    uint64_t sweep = 0;
+    long long launches = 0;
+    double last_sweep_ms = 0, last_energy_ms = 0;
+    long long last_tests = 0, last_evals = 0;
+    unsigned long long attr_set = 0;  // bitmask of k_sweep instantiations whose smem attribute is set
+    bool ktiming = false;
+    std::vector<cudaEvent_t> kev;  // event pool for per-kernel timing
+    std::vector<int> kev_kind;     // 0 sweep, 1 rebin (one entry per event PAIR used in this call)
+    double k_sweep_ms = 0, k_rebin_ms = 0;
+    long long k_sweep_launches = 0, k_rebin_launches = 0;
+
+#if MC2D_HAVE_NCCL_H
+    ncclComm_t comm = nullptr;
+#endif
+    bool have_comm = false;
+};
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            char b__[512];                                                                            \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            ctx->err = b__;                                                                           \
+            return MC2D_ERR_CUDA;                                                                     \
+        }                                                                                             \
+    } while (0)
+
+#define FAIL(code, ...)                           \
+    do {                                          \
+        char b__[512];                            \
+        snprintf(b__, sizeof b__, __VA_ARGS__);   \
+        ctx->err = b__;                           \
+        return (code);                            \
+    } while (0)
+
+#define DISPATCH_POT(pot, ...)                                                         \
+    switch (pot) {                                                                     \
+    case 0: { constexpr int POT = 0; __VA_ARGS__; } break;                             \
+    case 1: { constexpr int POT = 1; __VA_ARGS__; } break;                             \
+    case 2: { constexpr int POT = 2; __VA_ARGS__; } break;                             \
+    case 3: { constexpr int POT = 3; __VA_ARGS__; } break;                             \
+    case 4: { constexpr int POT = 4; __VA_ARGS__; } break;                             \
+    default: { constexpr int POT = 5; __VA_ARGS__; } break;                            \
+    }
+
+// ------------------------------------------------------------------------------------------------
+// pure host geometry
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *mc2d_status_string(int s) {
+    switch (s) {
+    case MC2D_OK: return "ok";
+    case MC2D_ERR_INVALID: return "invalid argument";
+    case MC2D_ERR_CUDA: return "CUDA error";
+    case MC2D_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+    case MC2D_ERR_CELL_OVERFLOW: return "cell capacity exceeded";
+    case MC2D_ERR_GEOMETRY: return "box too small for the checkerboard grid";
+    case MC2D_ERR_OUT_OF_BOX: return "position outside the box or NaN";
+    case MC2D_ERR_NCCL: return "NCCL error";
+    case MC2D_ERR_STATE: return "call out of order";
+    }
+    return "unknown status";
+}
+extern "C" const char *mc2d_last_error(const mc2d_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int mc2d_abi_version(void) { return MC2D_ABI_VERSION; }
+extern "C" int mc2d_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int mc2d_reference_grid(double Lx, double Ly, double rcut, int *nx, int *ny, double *cdx, double *cdy) {
+    if (!(Lx > 0) || !(Ly > 0) || !(rcut > 0)) return MC2D_ERR_INVALID;
+    int ix = (int)(Lx / rcut), iy = (int)(Ly / rcut);  // cell_list.cpp:8-13
+    if (ix < 1) ix = 1;
+    if (iy < 1) iy = 1;
+    if (nx) *nx = ix;
+    if (ny) *ny = iy;
+    if (cdx) *cdx = Lx / ix;
+    if (cdy) *cdy = Ly / iy;
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_sweep_grid(double Lx, double Ly, double rcut, int nranks, int *nx, int *ny, double *cdx,
+                               double *cdy) {
+    if (!(Lx > 0) || !(Ly > 0) || !(rcut > 0) || nranks < 1) return MC2D_ERR_INVALID;
+    long long ix = (long long)(Lx / rcut), iy = (long long)(Ly / rcut);
+    ix -= ix % (2LL * nranks);  // even count per slab (cell_list_parallel.cpp:97-105)
+    iy -= iy % 2;
+    if (ix < 2LL * nranks || iy < 2 || ix > (1 << 24) || iy > (1 << 24)) return MC2D_ERR_GEOMETRY;
+    if (nx) *nx = (int)ix;
+    if (ny) *ny = (int)iy;
+    if (cdx) *cdx = Lx / (double)ix;
+    if (cdy) *cdy = Ly / (double)iy;
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_slab_columns(int nx, int nranks, int rank, int *col0, int *ncol) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || nx < 2 * nranks || nx % (2 * nranks)) return MC2D_ERR_INVALID;
+    int per = nx / nranks;
+    if (col0) *col0 = rank * per;
+    if (ncol) *ncol = per;
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_halo_route(int colour, int rank, int nranks, int *send_left, int *send_to, int *recv_from) {
+    if (colour < 0 || colour > 3 || nranks < 1 || rank < 0 || rank >= nranks) return MC2D_ERR_INVALID;
+    int px = colour & 1;  // column parity of the active cells; a slab starts on an even column
+    int left = (rank + nranks - 1) % nranks, right = (rank + 1) % nranks;
+    if (send_left) *send_left = (px == 0);
+    if (send_to) *send_to = (px == 0) ? left : right;
+    if (recv_from) *recv_from = (px == 0) ? right : left;
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_sweep_schedule(uint64_t seed, uint64_t sweep, double cdx, double cdy, int shift_grid,
+                                   int order[4], double *sx, double *sy) {
+    double a, b;
+    mc2d_schedule(seed, sweep, cdx, cdy, shift_grid, order, &a, &b);
+    if (sx) *sx = a;
+    if (sy) *sy = b;
+    return MC2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------
+extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
+    if (!p || !out) return MC2D_ERR_INVALID;
+    *out = nullptr;
+    mc2d_ctx *ctx = new mc2d_ctx();
+    *out = ctx;  // returned even on failure so that mc2d_last_error works; caller destroys it
+    ctx->prm = *p;
+    if (!(p->Lx > 0) || !(p->Ly > 0) || !(p->rcut > 0) || p->potential < 0 || p->potential > 5 || p->nranks < 1 ||
+        p->rank < 0 || p->rank >= p->nranks || !(p->temperature > 0) || p->delta < 0 || p->activity < 0 ||
+        p->cell_capacity < 0)
+        FAIL(MC2D_ERR_INVALID, "mc2d_create: invalid parameters");
+    int ndev = mc2d_device_count();
+    if (ndev <= 0) FAIL(MC2D_ERR_NO_DEVICE, "mc2d_create: no CUDA device visible; this library has no CPU path");
+    if (p->device < 0 || p->device >= ndev) FAIL(MC2D_ERR_INVALID, "mc2d_create: device %d of %d", p->device, ndev);
+    ctx->dev = p->device;
+    ctx->pp = PairParams{p->f_prime, p->f_d_prime, p->kappa, p->alpha};
+    ctx->r2cut = p->rcut * p->rcut;
+    ctx->beta = 1.0 / p->temperature;
+    if (p->p_insert > 0 || p->p_delete > 0) {
+        if (p->p_insert != p->p_delete || p->p_insert + p->p_delete > 1.0)
+            FAIL(MC2D_ERR_INVALID, "p_insert must equal p_delete (detailed balance) and sum to <= 1");
+        ctx->p_ins = p->p_insert;
+        ctx->p_del = p->p_delete;
+    }
+    Grid &g = ctx->g;
+    int rc = mc2d_sweep_grid(p->Lx, p->Ly, p->rcut, p->nranks, &g.nx, &g.ny, &g.dx, &g.dy);
+    if (rc != MC2D_OK) {
+        // The calculator hooks (reference grid) still work on such a box; only the checkerboard
+        // step loop cannot run.  mc2d_upload / mc2d_run_sweeps report MC2D_ERR_GEOMETRY.
+        if (p->nranks > 1)
+            FAIL(rc, "box %g x %g cannot hold an even checkerboard of cells >= rcut=%g on %d slab(s)", p->Lx, p->Ly,
+                 p->rcut, p->nranks);
+        ctx->sweep_ok = false;
+        g.nx = g.ny = 2;
+        g.dx = p->Lx / 2;
+        g.dy = p->Ly / 2;
+    }
+    mc2d_slab_columns(g.nx, p->nranks, p->rank, &g.col0, &g.ncol);
+    g.ghost = p->nranks > 1 ? 1 : 0;
+    g.ncs = g.ncol + 2 * g.ghost;
+    g.K = 0;
+    g.Lx = p->Lx;
+    g.Ly = p->Ly;
+    g.ox = g.oy = 0.0;
+    CU(cudaSetDevice(ctx->dev));
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&ctx->ev0));
+    CU(cudaEventCreate(&ctx->ev1));
+    CU(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&ctx->d_energy, 4 * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_pair_stats, 4 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&ctx->d_err, 4 * sizeof(int)));
+    CU(cudaMalloc(&ctx->d_trace_n, sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_energy, 0, 4 * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MC2D_OK;
+}
+
+static void free_slots(mc2d_ctx *ctx) {
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->pos[b]) cudaFree(ctx->pos[b]);
+        if (ctx->cnt[b]) cudaFree(ctx->cnt[b]);
+        if (ctx->ids[b]) cudaFree(ctx->ids[b]);
+        ctx->pos[b] = nullptr;
+        ctx->cnt[b] = nullptr;
+        ctx->ids[b] = nullptr;
+    }
+    ctx->allocK = 0;
+}
+
+extern "C" int mc2d_destroy(mc2d_ctx *ctx) {
+    if (!ctx) return MC2D_OK;
+    if (ctx->stream) {
+        cudaSetDevice(ctx->dev);
+        cudaStreamSynchronize(ctx->stream);
+#if MC2D_HAVE_NCCL_H
+        if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+#endif
+        free_slots(ctx);
+        DevBuf *bufs[] = {&ctx->partial, &ctx->trace_buf, &ctx->xy_in, &ctx->ids_in, &ctx->keys, &ctx->keys_sorted,
+                          &ctx->idx, &ctx->idx_sorted, &ctx->spos, &ctx->sids, &ctx->start, &ctx->cub_tmp, &ctx->pts,
+                          &ctx->excl, &ctx->outE, &ctx->outC, &ctx->outI, &ctx->offsets};
+        for (DevBuf *b : bufs) b->release();
+        if (ctx->d_counters) cudaFree(ctx->d_counters);
+        if (ctx->d_energy) cudaFree(ctx->d_energy);
+        if (ctx->d_pair_stats) cudaFree(ctx->d_pair_stats);
+        if (ctx->d_err) cudaFree(ctx->d_err);
+        if (ctx->d_trace_n) cudaFree(ctx->d_trace_n);
+        if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+        if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+        for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+    return MC2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSR build: keys -> radix sort -> gather -> cell offsets   (K1)
+// ------------------------------------------------------------------------------------------------
+// mode 0: reference grid (nx,ny,cdx,cdy given); mode 1: checkerboard grid ctx->g, slab filter.
+// On return ctx->spos / ctx->sids (perm or ids) / ctx->start hold the CSR arrays; *n_kept = number of
+// particles with a real (non-sentinel) key.
+static int build_csr(mc2d_ctx *ctx, const double2 *d_xy, const int *d_ids, long long n, int mode, int nx, int ny,
+                     double cdx, double cdy, int ncell, long long *n_kept) {
+    const int nn = (int)n;
+    CU(ctx->keys.ensure(sizeof(int) * (size_t)(nn + 1)));
+    CU(ctx->keys_sorted.ensure(sizeof(int) * (size_t)(nn + 1)));
+    CU(ctx->idx.ensure(sizeof(int) * (size_t)(nn + 1)));
+    CU(ctx->idx_sorted.ensure(sizeof(int) * (size_t)(nn + 1)));
+    CU(ctx->spos.ensure(sizeof(double2) * (size_t)(nn + 1)));
+    CU(ctx->sids.ensure(sizeof(int) * (size_t)(nn + 1)));
+    CU(ctx->start.ensure(sizeof(int) * (size_t)(ncell + 2)));
+    CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
+    if (nn > 0) {
+        k_cell_keys<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(d_xy, nn, mode, nx, ny, cdx, cdy, ctx->prm.Lx,
+                                                               ctx->prm.Ly, ctx->g, ncell, ctx->keys.as<int>(),
+                                                               ctx->idx.as<int>(), ctx->d_err + 1);
+        ctx->launches++;
+        int end_bit = 1;
+        while ((1LL << end_bit) <= (long long)ncell) ++end_bit;
+        size_t tmp_bytes = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->keys.as<int>(), ctx->keys_sorted.as<int>(),
+                                           ctx->idx.as<int>(), ctx->idx_sorted.as<int>(), nn, 0, end_bit,
+                                           ctx->stream));
+        CU(ctx->cub_tmp.ensure(tmp_bytes));
+        CU(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, ctx->keys.as<int>(), ctx->keys_sorted.as<int>(),
+                                           ctx->idx.as<int>(), ctx->idx_sorted.as<int>(), nn, 0, end_bit,
+                                           ctx->stream));
+        ctx->launches += 3;
+        k_gather_sorted<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(d_xy, d_ids, ctx->idx_sorted.as<int>(), nn,
+                                                                   ctx->spos.as<double2>(), ctx->sids.as<int>());
+        ctx->launches++;
+    }
+    k_cell_bounds<<<(nn + 1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->keys_sorted.as<int>(), nn, ncell,
+                                                                 ctx->start.as<int>());
+    ctx->launches++;
+    int flags[4];
+    int kept = 0;
+    CU(cudaMemcpyAsync(flags, ctx->d_err, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&kept, ctx->start.as<int>() + ncell, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    if (flags[1] & 1) FAIL(MC2D_ERR_OUT_OF_BOX, "a position is NaN or outside [0,%g] x [0,%g]", ctx->prm.Lx, ctx->prm.Ly);
+    if (n_kept) *n_kept = kept;
+    return MC2D_OK;
+}
+
+static int h2d_positions(mc2d_ctx *ctx, const double *xy, long long n) {
+    if (n < 0 || n > 0x7ffffff0LL) FAIL(MC2D_ERR_INVALID, "particle count %lld out of range", n);
+    CU(cudaSetDevice(ctx->dev));
+    CU(ctx->xy_in.ensure(sizeof(double2) * (size_t)(n + 1)));
+    if (n > 0) CU(cudaMemcpyAsync(ctx->xy_in.p, xy, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    return MC2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// halo exchange (K5): a cell column is contiguous, so no pack kernel is needed
+// ------------------------------------------------------------------------------------------------
+static int halo_exchange(mc2d_ctx *ctx, int buf, bool left, bool right) {
+#if MC2D_HAVE_NCCL_H
+    const Grid &g = ctx->g;
+    if (!g.ghost) return MC2D_OK;
+    if (!ctx->have_comm) FAIL(MC2D_ERR_STATE, "nranks > 1 but mc2d_comm_init was not called");
+    const int R = ctx->prm.nranks, me = ctx->prm.rank;
+    const int lrank = (me + R - 1) % R, rrank = (me + 1) % R;
+    const size_t colp = (size_t)g.ny * g.K, colc = (size_t)g.ny;
+    auto col_pos = [&](int c) { return ctx->pos[buf] + (size_t)c * colp; };
+    auto col_cnt = [&](int c) { return ctx->cnt[buf] + (size_t)c * colc; };
+    auto col_ids = [&](int c) { return ctx->ids[buf] + (size_t)c * colp; };
+    const int first = g.ghost, last = g.ghost + g.ncol - 1, lghost = 0, rghost = g.ghost + g.ncol;
+#define NC(call)                                                                                  \
+    do {                                                                                          \
+        ncclResult_t r__ = (call);                                                                \
+        if (r__ != ncclSuccess) FAIL(MC2D_ERR_NCCL, "%s: %s", #call, g_nccl.GetErrorString(r__)); \
+    } while (0)
+    NC(g_nccl.GroupStart());
+    if (left) {  // my first owned column -> left neighbour's right ghost; my right ghost <- right neighbour
+        NC(g_nccl.Send(col_pos(first), colp * sizeof(double2), ncclChar, lrank, ctx->comm, ctx->stream));
+        NC(g_nccl.Send(col_cnt(first), colc * sizeof(int), ncclChar, lrank, ctx->comm, ctx->stream));
+        if (ctx->use_ids) NC(g_nccl.Send(col_ids(first), colp * sizeof(int), ncclChar, lrank, ctx->comm, ctx->stream));
+        NC(g_nccl.Recv(col_pos(rghost), colp * sizeof(double2), ncclChar, rrank, ctx->comm, ctx->stream));
+        NC(g_nccl.Recv(col_cnt(rghost), colc * sizeof(int), ncclChar, rrank, ctx->comm, ctx->stream));
+        if (ctx->use_ids) NC(g_nccl.Recv(col_ids(rghost), colp * sizeof(int), ncclChar, rrank, ctx->comm, ctx->stream));
+    }
+    if (right) {  // my last owned column -> right neighbour's left ghost; my left ghost <- left neighbour
+        NC(g_nccl.Send(col_pos(last), colp * sizeof(double2), ncclChar, rrank, ctx->comm, ctx->stream));
+        NC(g_nccl.Send(col_cnt(last), colc * sizeof(int), ncclChar, rrank, ctx->comm, ctx->stream));
+        if (ctx->use_ids) NC(g_nccl.Send(col_ids(last), colp * sizeof(int), ncclChar, rrank, ctx->comm, ctx->stream));
+        NC(g_nccl.Recv(col_pos(lghost), colp * sizeof(double2), ncclChar, lrank, ctx->comm, ctx->stream));
+        NC(g_nccl.Recv(col_cnt(lghost), colc * sizeof(int), ncclChar, lrank, ctx->comm, ctx->stream));
+        if (ctx->use_ids) NC(g_nccl.Recv(col_ids(lghost), colp * sizeof(int), ncclChar, lrank, ctx->comm, ctx->stream));
+    }
+    NC(g_nccl.GroupEnd());
+    return MC2D_OK;
+#else
+    (void)buf; (void)left; (void)right;
+    if (ctx->g.ghost) FAIL(MC2D_ERR_NCCL, "built without nccl.h");
+    return MC2D_OK;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// slot storage
+// ------------------------------------------------------------------------------------------------
+static int alloc_slots(mc2d_ctx *ctx, int K) {
+    free_slots(ctx);
+    const size_t ncell = (size_t)ctx->g.ncs * ctx->g.ny;
+    for (int b = 0; b < 2; ++b) {
+        CU(cudaMalloc(&ctx->pos[b], sizeof(double2) * ncell * K));
+        CU(cudaMalloc(&ctx->cnt[b], sizeof(int) * ncell));
+        CU(cudaMemsetAsync(ctx->cnt[b], 0, sizeof(int) * ncell, ctx->stream));
+        if (ctx->use_ids) CU(cudaMalloc(&ctx->ids[b], sizeof(int) * ncell * K));
+    }
+    ctx->allocK = K;
+    ctx->g.K = K;
+    return MC2D_OK;
+}
+
+static int auto_capacity(const mc2d_ctx *ctx, int maxcount) {
+    const Grid &g = ctx->g;
+    const double A = g.dx * g.dy;
+    double bound = 0.0;
+    switch (ctx->prm.potential) {
+    case MC2D_IDEAL: {
+        double m = ctx->prm.activity * A;
+        bound = m + 8.0 * sqrt(m) + 8.0;
+    } break;
+    case MC2D_LENNARD_JONES:
+    case MC2D_WCA: bound = 1.6 * A + 6.0; break;  // above 2D close packing of unit-diameter cores (1.155/sigma^2)
+    default: bound = 0.0;
+    }
+    int K = std::max(8, std::max(maxcount + maxcount / 2 + 4, (int)ceil(bound)));
+    if (ctx->prm.cell_capacity > 0) K = std::max(ctx->prm.cell_capacity, maxcount);
+    return even_up(K, 4);
+}
+
+static int energy_on_slots(mc2d_ctx *ctx, double *U, double *W, long long *N, bool resync, bool allreduce);
+
+extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long long n) {
+    if (!ctx || (n > 0 && !xy)) return MC2D_ERR_INVALID;
+    if (!ctx->sweep_ok)
+        FAIL(MC2D_ERR_GEOMETRY, "box %g x %g cannot hold an even checkerboard of cells >= rcut=%g (needs >= 2 cells per "
+             "direction); only the calculator hooks are available", ctx->prm.Lx, ctx->prm.Ly, ctx->prm.rcut);
+    int rc = h2d_positions(ctx, xy, n);
+    if (rc) return rc;
+    ctx->use_ids = (ids != nullptr);
+    if (ids) {
+        CU(ctx->ids_in.ensure(sizeof(int) * (size_t)(n + 1)));
+        if (n > 0) CU(cudaMemcpyAsync(ctx->ids_in.p, ids, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    Grid &g = ctx->g;
+    g.ox = g.oy = 0.0;
+    const int ncell = g.ncs * g.ny;
+    long long kept = 0;
+    rc = build_csr(ctx, ctx->xy_in.as<double2>(), ids ? ctx->ids_in.as<int>() : nullptr, n, 1, g.nx, g.ny, g.dx, g.dy,
+                   ncell, &kept);
+    if (rc) return rc;
+    k_max_cell_count<<<(ncell + 255) / 256, 256, 0, ctx->stream>>>(ctx->start.as<int>(), ncell, ctx->d_err + 2);
+    ctx->launches++;
+    int maxcount = 0;
+    CU(cudaMemcpyAsync(&maxcount, ctx->d_err + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    int K = auto_capacity(ctx, maxcount);
+    if (K > 1024) FAIL(MC2D_ERR_CELL_OVERFLOW, "a cell holds %d particles; capacity %d exceeds the 1024-slot limit", maxcount, K);
+    if (K != ctx->allocK || (ctx->use_ids && !ctx->ids[0])) {
+        rc = alloc_slots(ctx, K);
+        if (rc) return rc;
+    }
+    ctx->cur = 0;
+    CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
+    k_csr_to_slots<<<(ncell + 7) / 8, 256, 0, ctx->stream>>>(ctx->spos.as<double2>(), ctx->sids.as<int>(),
+                                                             ctx->start.as<int>(), ncell, g.K, ctx->pos[0],
+                                                             ctx->cnt[0], ctx->use_ids ? ctx->ids[0] : nullptr,
+                                                             ctx->d_err);
+    ctx->launches++;
+    ctx->have_particles = true;
+    ctx->sweep = 0;
+    CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    if (g.ghost && ctx->have_comm) {
+        rc = halo_exchange(ctx, ctx->cur, true, true);
+        if (rc) return rc;
+    }
+    if (!g.ghost || ctx->have_comm) {
+        double U, W;
+        long long N;
+        rc = energy_on_slots(ctx, &U, &W, &N, true, false);
+        if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return MC2D_OK;
+}
+
+static int count_particles(mc2d_ctx *ctx, long long *n) {
+    const Grid &g = ctx->g;
+    const int cell0 = g.ghost * g.ny, ncell = g.ncol * g.ny;
+    CU(cudaMemsetAsync(ctx->d_pair_stats + 2, 0, sizeof(unsigned long long), ctx->stream));
+    k_sum_counts<<<(ncell + 255) / 256, 256, 0, ctx->stream>>>(ctx->cnt[ctx->cur], cell0, ncell, ctx->d_pair_stats + 2);
+    ctx->launches++;
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, ctx->d_pair_stats + 2, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *n = (long long)v;
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_num_particles(mc2d_ctx *ctx, long long *n_local) {
+    if (!ctx || !n_local) return MC2D_ERR_INVALID;
+    if (!ctx->have_particles) FAIL(MC2D_ERR_STATE, "no particles uploaded");
+    CU(cudaSetDevice(ctx->dev));
+    return count_particles(ctx, n_local);
+}
+
+extern "C" int mc2d_download(mc2d_ctx *ctx, double *xy, int *ids, long long cap, long long *n_out) {
+    if (!ctx || !n_out) return MC2D_ERR_INVALID;
+    if (!ctx->have_particles) FAIL(MC2D_ERR_STATE, "no particles uploaded");
+    CU(cudaSetDevice(ctx->dev));
+    const Grid &g = ctx->g;
+    const int cell0 = g.ghost * g.ny, ncell = g.ncol * g.ny;
+    CU(ctx->offsets.ensure(sizeof(int) * (size_t)(ncell + 1)));
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->cnt[ctx->cur] + cell0, ctx->offsets.as<int>(), ncell,
+                                     ctx->stream));
+    CU(ctx->cub_tmp.ensure(tmp_bytes));
+    CU(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->cnt[ctx->cur] + cell0, ctx->offsets.as<int>(),
+                                     ncell, ctx->stream));
+    ctx->launches += 2;
+    long long n = 0;
+    int rc = count_particles(ctx, &n);
+    if (rc) return rc;
+    *n_out = n;
+    if (n > cap) FAIL(MC2D_ERR_INVALID, "download needs room for %lld particles, caller gave %lld", n, cap);
+    if (n == 0) return MC2D_OK;
+    CU(ctx->spos.ensure(sizeof(double2) * (size_t)n));
+    CU(ctx->sids.ensure(sizeof(int) * (size_t)n));
+    k_compact<<<(ncell + 7) / 8, 256, 0, ctx->stream>>>(ctx->pos[ctx->cur], ctx->cnt[ctx->cur],
+                                                        ctx->use_ids ? ctx->ids[ctx->cur] : nullptr,
+                                                        ctx->offsets.as<int>(), cell0, ncell, g.K,
+                                                        ctx->spos.as<double2>(), ids ? ctx->sids.as<int>() : nullptr);
+    ctx->launches++;
+    if (xy) CU(cudaMemcpyAsync(xy, ctx->spos.p, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ids) CU(cudaMemcpyAsync(ids, ctx->sids.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return MC2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 launches
+// ------------------------------------------------------------------------------------------------
+template <class V>
+static int launch_energy(mc2d_ctx *ctx, const V &view, int ncells, int half, bool perp, int *count_out,
+                         double *eloc_out, double *U, double *W) {
+    const int wpb = 8, nblocks = std::max(1, (ncells + wpb - 1) / wpb);
+    CU(ctx->partial.ensure(sizeof(double) * 2 * (size_t)nblocks));
+    double *pU = ctx->partial.as<double>(), *pW = pU + nblocks;
+    CU(cudaMemsetAsync(ctx->d_pair_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    DISPATCH_POT(ctx->prm.potential, {
+        if (perp)
+            k_energy_virial<V, POT, true><<<nblocks, wpb * 32, 0, ctx->stream>>>(
+                view, ctx->pp, ctx->r2cut, half, pU, pW, ctx->d_pair_stats, count_out, eloc_out);
+        else
+            k_energy_virial<V, POT, false><<<nblocks, wpb * 32, 0, ctx->stream>>>(
+                view, ctx->pp, ctx->r2cut, half, pU, pW, ctx->d_pair_stats, nullptr, nullptr);
+    });
+    const double scale = half ? 1.0 : 0.5;  // directed double count is halved (thermodynamic_calculator.cpp:211,232)
+    k_reduce_partials<<<1, 256, 0, ctx->stream>>>(pU, nblocks, scale, ctx->d_energy + 1, 0);
+    k_reduce_partials<<<1, 256, 0, ctx->stream>>>(pW, nblocks, scale, ctx->d_energy + 2, 0);
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->launches += 3;
+    double uw[2];
+    unsigned long long ps[2];
+    CU(cudaMemcpyAsync(uw, ctx->d_energy + 1, sizeof uw, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ps, ctx->d_pair_stats, sizeof ps, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_energy_ms = ms;
+    ctx->last_tests = (long long)ps[0];
+    ctx->last_evals = (long long)ps[1];
+    *U = uw[0];
+    *W = uw[1];
+    return MC2D_OK;
+}
+
+static int energy_on_slots(mc2d_ctx *ctx, double *U, double *W, long long *N, bool resync, bool allreduce) {
+    const Grid &g = ctx->g;
+    SlotView v{ctx->pos[ctx->cur], ctx->cnt[ctx->cur], g};
+    const int half = (g.nx >= 3 && g.ny >= 3) ? 1 : 0;
+    int rc = launch_energy(ctx, v, g.ncol * g.ny, half, false, nullptr, nullptr, U, W);
+    if (rc) return rc;
+    long long n = 0;
+    rc = count_particles(ctx, &n);
+    if (rc) return rc;
+    if (resync) CU(cudaMemcpyAsync(ctx->d_energy, ctx->d_energy + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (allreduce && ctx->g.ghost) {
+#if MC2D_HAVE_NCCL_H
+        if (!ctx->have_comm) FAIL(MC2D_ERR_STATE, "allreduce requested without a communicator");
+        double h[3] = {*U, *W, (double)n};
+        CU(cudaMemcpyAsync(ctx->d_energy + 1, h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+        ncclResult_t r = g_nccl.AllReduce(ctx->d_energy + 1, ctx->d_energy + 1, 3, ncclDouble, ncclSum, ctx->comm,
+                                          ctx->stream);
+        if (r != ncclSuccess) FAIL(MC2D_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+        CU(cudaMemcpyAsync(h, ctx->d_energy + 1, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        *U = h[0];
+        *W = h[1];
+        n = (long long)llround(h[2]);
+#endif
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (N) *N = n;
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_total_energy_virial(mc2d_ctx *ctx, int resync, int allreduce, double *U, double *W, long long *N) {
+    if (!ctx) return MC2D_ERR_INVALID;
+    if (!ctx->have_particles) FAIL(MC2D_ERR_STATE, "no particles uploaded");
+    CU(cudaSetDevice(ctx->dev));
+    double u, w;
+    long long n;
+    int rc = energy_on_slots(ctx, &u, &w, &n, resync != 0, allreduce != 0);
+    if (rc) return rc;
+    if (U) *U = u;
+    if (W) *W = w;
+    if (N) *N = n;
+    return MC2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ThermodynamicCalculator / CellList hooks on the reference grid
+// ------------------------------------------------------------------------------------------------
+static int build_reference_csr(mc2d_ctx *ctx, const double *xy, long long n, CsrView *view) {
+    int nx, ny;
+    double cdx, cdy;
+    mc2d_reference_grid(ctx->prm.Lx, ctx->prm.Ly, ctx->prm.rcut, &nx, &ny, &cdx, &cdy);
+    if ((long long)nx * ny > 0x3fffffffLL) FAIL(MC2D_ERR_GEOMETRY, "reference grid %d x %d too large", nx, ny);
+    int rc = h2d_positions(ctx, xy, n);
+    if (rc) return rc;
+    long long kept = 0;
+    rc = build_csr(ctx, ctx->xy_in.as<double2>(), nullptr, n, 0, nx, ny, cdx, cdy, nx * ny, &kept);
+    if (rc) return rc;
+    *view = CsrView{ctx->spos.as<double2>(), ctx->sids.as<int>(), ctx->start.as<int>(), nx, ny, cdx, cdy,
+                    ctx->prm.Lx, ctx->prm.Ly};
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_calc_energy_virial(mc2d_ctx *ctx, const double *xy, long long n, double *U, double *W) {
+    if (!ctx || (n > 0 && !xy)) return MC2D_ERR_INVALID;
+    CsrView v;
+    int rc = build_reference_csr(ctx, xy, n, &v);
+    if (rc) return rc;
+    double u = 0, w = 0;
+    const int half = (v.nx >= 3 && v.ny >= 3) ? 1 : 0;
+    rc = launch_energy(ctx, v, v.nx * v.ny, half, false, nullptr, nullptr, &u, &w);
+    if (rc) return rc;
+    if (U) *U = u;
+    if (W) *W = w;
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_calc_cell_ids(mc2d_ctx *ctx, const double *xy, long long n, int *cell_out) {
+    if (!ctx || (n > 0 && (!xy || !cell_out))) return MC2D_ERR_INVALID;
+    int nx, ny;
+    double cdx, cdy;
+    mc2d_reference_grid(ctx->prm.Lx, ctx->prm.Ly, ctx->prm.rcut, &nx, &ny, &cdx, &cdy);
+    int rc = h2d_positions(ctx, xy, n);
+    if (rc) return rc;
+    if (n == 0) return MC2D_OK;
+    const int nn = (int)n;
+    CU(ctx->keys.ensure(sizeof(int) * (size_t)nn));
+    CU(ctx->idx.ensure(sizeof(int) * (size_t)nn));
+    CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
+    k_cell_keys<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(ctx->xy_in.as<double2>(), nn, 0, nx, ny, cdx, cdy,
+                                                           ctx->prm.Lx, ctx->prm.Ly, ctx->g, nx * ny,
+                                                           ctx->keys.as<int>(), ctx->idx.as<int>(), ctx->d_err + 1);
+    ctx->launches++;
+    CU(cudaMemcpyAsync(cell_out, ctx->keys.p, sizeof(int) * (size_t)nn, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_calc_neighbor_counts(mc2d_ctx *ctx, const double *xy, long long n, int *count_out,
+                                         double *local_energy_out) {
+    if (!ctx || (n > 0 && (!xy || !count_out))) return MC2D_ERR_INVALID;
+    CsrView v;
+    int rc = build_reference_csr(ctx, xy, n, &v);
+    if (rc) return rc;
+    if (n == 0) return MC2D_OK;
+    CU(ctx->outC.ensure(sizeof(int) * (size_t)n));
+    CU(ctx->outE.ensure(sizeof(double) * (size_t)n));
+    CU(cudaMemsetAsync(ctx->outC.p, 0, sizeof(int) * (size_t)n, ctx->stream));
+    double u, w;
+    rc = launch_energy(ctx, v, v.nx * v.ny, 0, true, ctx->outC.as<int>(), ctx->outE.as<double>(), &u, &w);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(count_out, ctx->outC.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (local_energy_out)
+        CU(cudaMemcpyAsync(local_energy_out, ctx->outE.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_calc_point_energies(mc2d_ctx *ctx, const double *xy, long long n, const double *points,
+                                        const int *exclude, long long nq, double *energy_out, int *count_out) {
+    if (!ctx || (n > 0 && !xy) || nq < 0 || (nq > 0 && (!points || !energy_out))) return MC2D_ERR_INVALID;
+    CsrView v;
+    int rc = build_reference_csr(ctx, xy, n, &v);
+    if (rc) return rc;
+    if (nq == 0) return MC2D_OK;
+    CU(ctx->pts.ensure(sizeof(double2) * (size_t)nq));
+    CU(ctx->excl.ensure(sizeof(int) * (size_t)nq));
+    CU(ctx->outE.ensure(sizeof(double) * (size_t)nq));
+    CU(ctx->outC.ensure(sizeof(int) * (size_t)nq));
+    CU(cudaMemcpyAsync(ctx->pts.p, points, sizeof(double2) * (size_t)nq, cudaMemcpyHostToDevice, ctx->stream));
+    if (exclude) CU(cudaMemcpyAsync(ctx->excl.p, exclude, sizeof(int) * (size_t)nq, cudaMemcpyHostToDevice, ctx->stream));
+    const int q = (int)nq;
+    DISPATCH_POT(ctx->prm.potential, {
+        k_point_energy<POT><<<(q + 7) / 8, 256, 0, ctx->stream>>>(v, ctx->pp, ctx->r2cut, ctx->pts.as<double2>(),
+                                                                  exclude ? ctx->excl.as<int>() : nullptr, q,
+                                                                  ctx->outE.as<double>(), ctx->outC.as<int>());
+    });
+    ctx->launches++;
+    CU(cudaMemcpyAsync(energy_out, ctx->outE.p, sizeof(double) * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
+    if (count_out) CU(cudaMemcpyAsync(count_out, ctx->outC.p, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return MC2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the step loop
+// ------------------------------------------------------------------------------------------------
+template <int POT, bool MINIMG, bool TRACE>
+static int launch_sweep_kernel(mc2d_ctx *ctx, const SweepArgs &a, int nblocks, int wpb, size_t smem, int inst) {
+    if (!(ctx->attr_set & (1ull << inst))) {
+        CU(cudaFuncSetAttribute(k_sweep<POT, MINIMG, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ctx->attr_set |= (1ull << inst);
+    }
+    k_sweep<POT, MINIMG, TRACE><<<nblocks, wpb * 32, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    return MC2D_OK;
+}
+
+static int ktime_begin(mc2d_ctx *ctx, int kind) {
+    if (!ctx->ktiming) return MC2D_OK;
+    const size_t need = 2 * (ctx->kev_kind.size() + 1);
+    while (ctx->kev.size() < need) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        ctx->kev.push_back(e);
+    }
+    ctx->kev_kind.push_back(kind);
+    CU(cudaEventRecord(ctx->kev[need - 2], ctx->stream));
+    return MC2D_OK;
+}
+static int ktime_end(mc2d_ctx *ctx) {
+    if (!ctx->ktiming) return MC2D_OK;
+    CU(cudaEventRecord(ctx->kev[2 * ctx->kev_kind.size() - 1], ctx->stream));
+    return MC2D_OK;
+}
+
+static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_plan *plan, mc2d_trial *trace,
+                           long long trace_cap, long long *trace_n) {
+    if (!ctx->have_particles) FAIL(MC2D_ERR_STATE, "no particles uploaded");
+    if (!plan || plan->disp_per_particle < 0 || plan->gc_per_cell < 0 || nsweeps < 0)
+        FAIL(MC2D_ERR_INVALID, "bad sweep plan");
+    if (plan->disp_per_particle * 1024LL + plan->gc_per_cell >= (1 << 28))
+        FAIL(MC2D_ERR_INVALID, "too many trials per cell visit");
+    CU(cudaSetDevice(ctx->dev));
+    Grid &g = ctx->g;
+    const int K = g.K;
+    const bool ideal = ctx->prm.potential == MC2D_IDEAL;
+    const bool minimg = (g.nx < 4 || g.ny < 4);
+    const size_t per_warp = (size_t)(K + (ideal ? 0 : 8 * K)) * sizeof(double2) + (size_t)K * sizeof(int);
+    int wpb = 8;
+    while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+    if (per_warp * wpb > 200 * 1024) FAIL(MC2D_ERR_CELL_OVERFLOW, "cell capacity %d needs too much shared memory", K);
+    const int nact = (g.ncol / 2) * (g.ny / 2);
+    const int nblocks = std::max(1, (nact + wpb - 1) / wpb);
+    CU(ctx->partial.ensure(sizeof(double) * 4 * (size_t)nblocks));
+    if (trace) {
+        CU(ctx->trace_buf.ensure(sizeof(mc2d_trial) * (size_t)trace_cap));
+        CU(cudaMemsetAsync(ctx->d_trace_n, 0, sizeof(unsigned long long), ctx->stream));
+    }
+    const int ncell_owned = g.ncol * g.ny;
+    ctx->kev_kind.clear();
+    CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (long long s = 0; s < nsweeps; ++s) {
+        int order[4];
+        double sx, sy;
+        mc2d_schedule(ctx->prm.seed, ctx->sweep, g.dx, g.dy, plan->shift_grid, order, &sx, &sy);
+        if (sx != g.ox || sy != g.oy) {
+            Grid gn = g;
+            gn.ox = sx;
+            gn.oy = sy;
+            const int nb = 1 - ctx->cur;
+            if (int rc = ktime_begin(ctx, 1)) return rc;
+            k_rebin<<<(ncell_owned + 7) / 8, 256, 0, ctx->stream>>>(ctx->pos[ctx->cur], ctx->cnt[ctx->cur],
+                                                                    ctx->use_ids ? ctx->ids[ctx->cur] : nullptr,
+                                                                    ctx->pos[nb], ctx->cnt[nb],
+                                                                    ctx->use_ids ? ctx->ids[nb] : nullptr, g, gn,
+                                                                    ctx->d_err);
+            if (int rc = ktime_end(ctx)) return rc;
+            ctx->launches++;
+            ctx->cur = nb;
+            g = gn;
+            int rc = halo_exchange(ctx, ctx->cur, true, true);
+            if (rc) return rc;
+        }
+        for (int p = 0; p < 4; ++p) {
+            SweepArgs a;
+            a.pos = ctx->pos[ctx->cur];
+            a.cnt = ctx->cnt[ctx->cur];
+            a.ids = ctx->use_ids ? ctx->ids[ctx->cur] : nullptr;
+            a.g = g;
+            a.pp = ctx->pp;
+            a.r2cut = ctx->r2cut;
+            a.beta = ctx->beta;
+            a.zA = ctx->prm.activity * g.dx * g.dy;
+            a.delta = ctx->prm.delta;
+            a.colour = order[p];
+            a.pass = p;
+            a.sweep_lo = (uint32_t)ctx->sweep;
+            a.sweep_hi = (uint32_t)(ctx->sweep >> 32);
+            a.seed_lo = (uint32_t)ctx->prm.seed;
+            a.seed_hi = (uint32_t)(ctx->prm.seed >> 32);
+            a.disp_mult = plan->disp_per_particle;
+            a.n_gc = plan->gc_per_cell;
+            a.p_ins = ctx->p_ins;
+            a.p_del = ctx->p_del;
+            a.partial_dU = ctx->partial.as<double>() + (size_t)p * nblocks;
+            a.counters = ctx->d_counters;
+            a.trace = trace ? ctx->trace_buf.as<mc2d_trial>() : nullptr;
+            a.trace_n = ctx->d_trace_n;
+            a.trace_cap = trace_cap;
+            const size_t smem = per_warp * wpb;
+            int rc = ktime_begin(ctx, 0);
+            if (rc) return rc;
+            const int pot = ctx->prm.potential;
+            DISPATCH_POT(pot, {
+                const int inst = POT * 4 + (minimg ? 2 : 0) + (trace ? 1 : 0);
+                if (trace) {
+                    if (minimg) rc = launch_sweep_kernel<POT, true, true>(ctx, a, nblocks, wpb, smem, inst);
+                    else rc = launch_sweep_kernel<POT, false, true>(ctx, a, nblocks, wpb, smem, inst);
+                } else {
+                    if (minimg) rc = launch_sweep_kernel<POT, true, false>(ctx, a, nblocks, wpb, smem, inst);
+                    else rc = launch_sweep_kernel<POT, false, false>(ctx, a, nblocks, wpb, smem, inst);
+                }
+            });
+            if (rc) return rc;
+            if ((rc = ktime_end(ctx))) return rc;
+            if (g.ghost) {
+                const bool left = (order[p] & 1) == 0;
+                rc = halo_exchange(ctx, ctx->cur, left, !left);
+                if (rc) return rc;
+            }
+        }
+        k_reduce_partials<<<1, 256, 0, ctx->stream>>>(ctx->partial.as<double>(), 4 * nblocks, 1.0, ctx->d_energy, 1);
+        ctx->launches++;
+        ctx->sweep++;
+    }
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    int errv[4];
+    CU(cudaMemcpyAsync(errv, ctx->d_err, sizeof errv, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long tn = 0;
+    if (trace) CU(cudaMemcpyAsync(&tn, ctx->d_trace_n, sizeof tn, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_sweep_ms = ms;
+    if (ctx->ktiming) {
+        ctx->k_sweep_ms = ctx->k_rebin_ms = 0;
+        ctx->k_sweep_launches = ctx->k_rebin_launches = 0;
+        for (size_t i = 0; i < ctx->kev_kind.size(); ++i) {
+            float t = 0;
+            CU(cudaEventElapsedTime(&t, ctx->kev[2 * i], ctx->kev[2 * i + 1]));
+            if (ctx->kev_kind[i] == 0) {
+                ctx->k_sweep_ms += t;
+                ctx->k_sweep_launches++;
+            } else {
+                ctx->k_rebin_ms += t;
+                ctx->k_rebin_launches++;
+            }
+        }
+    }
+    if (trace) {
+        long long ncopy = std::min<long long>((long long)tn, trace_cap);
+        if (ncopy > 0) CU(cudaMemcpy(trace, ctx->trace_buf.p, sizeof(mc2d_trial) * (size_t)ncopy, cudaMemcpyDeviceToHost));
+        if (trace_n) *trace_n = (long long)tn;
+    }
+    if (errv[0] > K)
+        FAIL(MC2D_ERR_CELL_OVERFLOW,
+             "re-binning needed %d slots in one cell but cell_capacity is %d: particles were dropped, the "
+             "configuration on the device is no longer valid; re-upload with a larger cell_capacity",
+             errv[0], K);
+    return MC2D_OK;
+}
+
+static int fetch_stats(mc2d_ctx *ctx, mc2d_stats *st) {
+    unsigned long long c[8];
+    double e = 0;
+    CU(cudaMemcpyAsync(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&e, ctx->d_energy, sizeof e, cudaMemcpyDeviceToHost, ctx->stream));
+    long long n = 0;
+    int rc = count_particles(ctx, &n);
+    if (rc) return rc;
+    for (int i = 0; i < 3; ++i) {
+        st->attempted[i] = (long long)c[i];
+        st->accepted[i] = (long long)c[3 + i];
+    }
+    st->overflow = (long long)c[6];
+    st->n_particles = n;
+    st->energy = e;
+    st->sweeps_done = ctx->sweep;
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_run_sweeps(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_plan *plan, mc2d_stats *st) {
+    if (!ctx) return MC2D_ERR_INVALID;
+    int rc = run_sweeps_impl(ctx, nsweeps, plan, nullptr, 0, nullptr);
+    if (rc) return rc;
+    if (st) {
+        rc = fetch_stats(ctx, st);
+        if (rc) return rc;
+        if (st->overflow > 0)
+            FAIL(MC2D_ERR_CELL_OVERFLOW, "%lld insertion(s) were refused because a cell had no free slot (capacity %d)",
+                 st->overflow, ctx->g.K);
+    }
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_run_sweep_traced(mc2d_ctx *ctx, const mc2d_sweep_plan *plan, mc2d_trial *trials, long long cap,
+                                     long long *n_out, mc2d_stats *st) {
+    if (!ctx || !trials || cap <= 0) return MC2D_ERR_INVALID;
+    int rc = run_sweeps_impl(ctx, 1, plan, trials, cap, n_out);
+    if (rc) return rc;
+    if (st) return fetch_stats(ctx, st);
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_get_stats(mc2d_ctx *ctx, mc2d_stats *st) {
+    if (!ctx || !st) return MC2D_ERR_INVALID;
+    if (!ctx->have_particles) FAIL(MC2D_ERR_STATE, "no particles uploaded");
+    CU(cudaSetDevice(ctx->dev));
+    return fetch_stats(ctx, st);
+}
+
+extern "C" int mc2d_reset_counters(mc2d_ctx *ctx) {
+    if (!ctx) return MC2D_ERR_INVALID;
+    CU(cudaSetDevice(ctx->dev));
+    CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_set_delta(mc2d_ctx *ctx, double delta) {
+    if (!ctx || !(delta >= 0)) return MC2D_ERR_INVALID;
+    ctx->prm.delta = delta;
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_set_activity(mc2d_ctx *ctx, double z) {
+    if (!ctx || !(z >= 0)) return MC2D_ERR_INVALID;
+    ctx->prm.activity = z;
+    return MC2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU
+// ------------------------------------------------------------------------------------------------
+extern "C" int mc2d_comm_unique_id(void *id_out) {
+#if MC2D_HAVE_NCCL_H
+    static_assert(sizeof(ncclUniqueId) == MC2D_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    std::string err;
+    if (!id_out || !g_nccl.load(err)) return MC2D_ERR_NCCL;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return MC2D_ERR_NCCL;
+    memcpy(id_out, &id, sizeof id);
+    return MC2D_OK;
+#else
+    (void)id_out;
+    return MC2D_ERR_NCCL;
+#endif
+}
+
+extern "C" int mc2d_comm_init(mc2d_ctx *ctx, const void *unique_id) {
+    if (!ctx || !unique_id) return MC2D_ERR_INVALID;
+#if MC2D_HAVE_NCCL_H
+    if (!g_nccl.load(ctx->err)) return MC2D_ERR_NCCL;
+    CU(cudaSetDevice(ctx->dev));
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof id);
+    ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, ctx->prm.nranks, id, ctx->prm.rank);
+    if (r != ncclSuccess) FAIL(MC2D_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+    ctx->have_comm = true;
+    if (ctx->have_particles && ctx->g.ghost) {  // particles were uploaded before the communicator existed
+        int rc = halo_exchange(ctx, ctx->cur, true, true);
+        if (rc) return rc;
+        double U, W;
+        long long N;
+        rc = energy_on_slots(ctx, &U, &W, &N, true, false);
+        if (rc) return rc;
+    }
+    return MC2D_OK;
+#else
+    FAIL(MC2D_ERR_NCCL, "built without nccl.h");
+#endif
+}
+
+extern "C" int mc2d_allreduce_stats(mc2d_ctx *ctx, mc2d_stats *st) {
+    if (!ctx || !st) return MC2D_ERR_INVALID;
+    if (ctx->prm.nranks == 1) return MC2D_OK;
+#if MC2D_HAVE_NCCL_H
+    if (!ctx->have_comm) FAIL(MC2D_ERR_STATE, "no communicator");
+    CU(cudaSetDevice(ctx->dev));
+    double h[9];
+    for (int i = 0; i < 3; ++i) {
+        h[i] = (double)st->attempted[i];
+        h[3 + i] = (double)st->accepted[i];
+    }
+    h[6] = (double)st->n_particles;
+    h[7] = st->energy;
+    h[8] = (double)st->overflow;
+    CU(ctx->outE.ensure(sizeof h));
+    CU(cudaMemcpyAsync(ctx->outE.p, h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+    ncclResult_t r = g_nccl.AllReduce(ctx->outE.p, ctx->outE.p, 9, ncclDouble, ncclSum, ctx->comm, ctx->stream);
+    if (r != ncclSuccess) FAIL(MC2D_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+    CU(cudaMemcpyAsync(h, ctx->outE.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 3; ++i) {
+        st->attempted[i] = llround(h[i]);
+        st->accepted[i] = llround(h[3 + i]);
+    }
+    st->n_particles = llround(h[6]);
+    st->energy = h[7];
+    st->overflow = llround(h[8]);
+    return MC2D_OK;
+#else
+    FAIL(MC2D_ERR_NCCL, "built without nccl.h");
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// introspection
+// ------------------------------------------------------------------------------------------------
+extern "C" int mc2d_get_info(mc2d_ctx *ctx, mc2d_info *o) {
+    if (!ctx || !o) return MC2D_ERR_INVALID;
+    const Grid &g = ctx->g;
+    o->nx = g.nx;
+    o->ny = g.ny;
+    o->col0 = g.col0;
+    o->ncol = g.ncol;
+    o->cell_capacity = g.K;
+    o->cell_dx = g.dx;
+    o->cell_dy = g.dy;
+    o->launches = ctx->launches;
+    o->last_sweep_ms = ctx->last_sweep_ms;
+    o->last_energy_ms = ctx->last_energy_ms;
+    o->last_pair_tests = ctx->last_tests;
+    o->last_pair_evals = ctx->last_evals;
+    o->k_sweep_ms = ctx->k_sweep_ms;
+    o->k_sweep_launches = ctx->k_sweep_launches;
+    o->k_rebin_ms = ctx->k_rebin_ms;
+    o->k_rebin_launches = ctx->k_rebin_launches;
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_set_kernel_timing(mc2d_ctx *ctx, int on) {
+    if (!ctx) return MC2D_ERR_INVALID;
+    ctx->ktiming = on != 0;
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_get_stream(mc2d_ctx *ctx, void **s) {
+    if (!ctx || !s) return MC2D_ERR_INVALID;
+    *s = (void *)ctx->stream;
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_synchronize(mc2d_ctx *ctx) {
+    if (!ctx) return MC2D_ERR_INVALID;
+    CU(cudaSetDevice(ctx->dev));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MC2D_OK;
+}

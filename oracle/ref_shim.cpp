@@ -253,6 +253,28 @@ double ref_time_mc_run(void *h, size_t nSteps, size_t fUpdateCell, long long *mo
     *moves = m->mc->simulation_step_time - t0;
     return std::chrono::duration<double>(b - a).count();
 }
+// The reference's move functions alone (no logging, no energy re-sync): per sweep N calls of
+// displacementMove_cell_list_dE (via stepCellList), one grandCanonicalMove when gcmc != 0, and a
+// cell rebuild every fUpdateCell sweeps — the most favourable way to time the reference's
+// "attempted moves per second".  Returns wall seconds; *moves = trials performed.
+double ref_time_moves(void *h, size_t nSweeps, size_t fUpdateCell, int gcmc, long long *moves) {
+    RefMC *m = static_cast<RefMC *>(h);
+    long long done = 0;
+    auto a = std::chrono::steady_clock::now();
+    for (size_t s = 0; s < nSweeps; ++s) {
+        size_t N = m->particles.size();
+        for (size_t i = 0; i < N; ++i) m->mc->stepCellList();
+        done += (long long)N;
+        if (gcmc) {
+            m->mc->grandCanonicalMove();
+            done += 1;
+        }
+        if (fUpdateCell && s % fUpdateCell == 0) m->mc->updateCellList();
+    }
+    auto b = std::chrono::steady_clock::now();
+    *moves = done;
+    return std::chrono::duration<double>(b - a).count();
+}
 // One computeTotalEnergyCellList + computeTotalVirialCellList pass; returns wall seconds.
 double ref_time_energy_virial(double T, int type, double rcut, double f, double alpha, double A0, double kappa,
                               double Lx, double Ly, const double *xy, int N, double *U, double *W) {

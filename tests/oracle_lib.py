@@ -335,6 +335,8 @@ class Ref:
         L.ref_mc_get_particles.argtypes = [C.c_void_p, c_double_p]
         L.ref_time_mc_run.restype = d
         L.ref_time_mc_run.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, c_ll_p]
+        L.ref_time_moves.restype = d
+        L.ref_time_moves.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, i, c_ll_p]
         L.ref_time_energy_virial.restype = d
         L.ref_time_energy_virial.argtypes = [d, i, d, d, d, d, d, d, d, c_double_p, i, c_double_p, c_double_p]
 
@@ -396,6 +398,11 @@ class Ref:
     def time_mc_run(self, mc: _MC, nsteps, fupdate):
         moves = C.c_longlong()
         s = self.lib.ref_time_mc_run(mc.h, nsteps, fupdate, C.byref(moves))
+        return s, moves.value
+
+    def time_moves(self, mc: _MC, nsweeps, fupdate, gcmc):
+        moves = C.c_longlong()
+        s = self.lib.ref_time_moves(mc.h, nsweeps, fupdate, int(gcmc), C.byref(moves))
         return s, moves.value
 
     def time_energy_virial(self, Lx, Ly, xy, *, T=1.0, ptype=LJ, rcut=2.5, f=0.0, alpha=0.0, A0=0.0, kappa=0.0):

@@ -1,0 +1,457 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/mc2d.h), against the CPU
+oracle on the same seeded inputs, against the committed golden fixtures, and — at the BASELINE
+sizes — through size-independent properties.
+
+Tolerances (BASELINE.json north_star): total energy, virial and per-trial dE within 1e-10
+relative (fp64); cell assignment and neighbour counts bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def mc():
+    import montecarlo_simulation_b200 as m
+    from montecarlo_simulation_b200 import api
+
+    assert api.device_count() > 0, "GPU tests need a CUDA device; libmc2d has no CPU fallback"
+    return m
+
+
+def lattice(n_side_x, n_side_y, Lx, Ly, jitter, seed):
+    rng = np.random.default_rng(seed)
+    g = np.stack(np.meshgrid(np.arange(n_side_x), np.arange(n_side_y), indexing="ij"), -1).reshape(-1, 2).astype(float)
+    xy = (g + 0.5) * np.array([Lx / n_side_x, Ly / n_side_y]) + rng.uniform(-jitter, jitter, size=g.shape)
+    xy[:, 0] %= Lx
+    xy[:, 1] %= Ly
+    return np.ascontiguousarray(xy)
+
+
+def relerr(a, b):
+    return abs(a - b) / max(1.0, abs(b))
+
+
+POTS = [
+    ("LennardJones", ol.LJ, dict(rcut=2.5)),
+    ("WCA", ol.WCA, dict(rcut=2 ** (1 / 6))),
+    ("Yukawa", ol.YUKAWA, dict(rcut=2.5)),
+    ("AthermalStar", ol.ATHERMAL_STAR, dict(rcut=2.5, f=8.0, alpha=0.3)),
+    ("ThermalStar", ol.THERMAL_STAR, dict(rcut=2.5, f=6.0, alpha=0.4, A0=1.5, kappa=1.1)),
+    ("Ideal", ol.IDEAL, dict(rcut=2.5)),
+]
+
+
+def make_pair(mc, oracle, name, ptype, kw, Lx, Ly, T=1.0, z=0.0, **ctx_kw):
+    k = dict(f=0.0, alpha=0.0, A0=0.0, kappa=0.0)
+    k.update(kw)
+    ctx = mc.Context(Lx, Ly, k["rcut"], potential=name, T=T, activity=z, f=k["f"], alpha=k["alpha"], A0=k["A0"],
+                     kappa=k["kappa"], **ctx_kw)
+    calc = oracle.calc(T, 0.0, ptype, k["rcut"], z, k["f"], k["alpha"], k["A0"], k["kappa"])
+    return ctx, calc
+
+
+# ---- cell assignment and neighbour counts: bit-exact ---------------------------------------------
+
+@pytest.mark.parametrize("Lx,Ly,rcut", [(31.0, 26.0, 2.5), (10.0, 10.0, 2.5), (9.306, 10.746, 2.5), (7.3, 4.9, 2.5),
+                                         (3.0, 3.0, 5.0), (45.254834, 45.254834, 2.5), (100.0, 10.0, 2.5)])
+def test_cell_ids_and_neighbor_counts_bit_exact(mc, oracle, Lx, Ly, rcut):
+    rng = np.random.default_rng(3)
+    xy = rng.uniform(0, 1, (2000, 2)) * [Lx, Ly]
+    xy[0] = [0.0, 0.0]
+    xy[1] = [np.nextafter(Lx, 0), np.nextafter(Ly, 0)]
+    xy[2] = [Lx, Ly]  # applyPBC can return exactly L (initial.cpp:22-25)
+    # put particles exactly on cell boundaries
+    nx, ny, dx, dy = oracle.cell_dims(Lx, Ly, rcut)
+    for k in range(min(nx, 8)):
+        xy[10 + k] = [k * dx, (k % ny) * dy]
+    with mc.Context(Lx, Ly, rcut) as ctx:
+        assert (ctx.calc_cell_ids(xy) == oracle.cell_ids(Lx, Ly, rcut, xy)).all()
+        cnt, eloc = ctx.calc_neighbor_counts(xy, with_energy=True)
+        assert (cnt == oracle.neighbor_counts(Lx, Ly, rcut, xy)).all()
+
+
+def test_inclusive_cutoff_exactly_at_rcut(mc, oracle):
+    """test_cell_list.cpp:32-53: a pair at exactly r = rcut is a neighbour; just beyond is not."""
+    P = np.array([[1.0, 1.0], [2.0, 1.0], [3.1, 1.0], [4.1 + 1e-12, 1.0]])
+    with mc.Context(5.0, 5.0, 1.0) as ctx:
+        cnt = ctx.calc_neighbor_counts(P)
+    assert cnt.tolist() == oracle.neighbor_counts(5.0, 5.0, 1.0, P).tolist() == [1, 1, 0, 0]
+
+
+# ---- U, W on the reference grid vs the oracle ------------------------------------------------------
+
+@pytest.mark.parametrize("name,ptype,kw", POTS)
+def test_energy_virial_vs_oracle(mc, oracle, name, ptype, kw):
+    Lx, Ly = 61.0, 47.5
+    xy = lattice(48, 40, Lx, Ly, 0.25, 100 + ptype)
+    ctx, calc = make_pair(mc, oracle, name, ptype, kw, Lx, Ly, T=1.3)
+    with ctx:
+        U, W = ctx.calc_energy_virial(xy)
+        Uo = oracle.total_energy_celllist(calc, Lx, Ly, xy)
+        Wo = oracle.total_virial_celllist(calc, Lx, Ly, xy)
+        assert relerr(U, Uo) < REL and relerr(W, Wo) < REL
+        assert relerr(ctx.calc_pressure(xy), oracle.pressure_celllist(calc, Lx, Ly, xy)) < REL
+        # per-particle local energies (computeLocalEnergy over getNeighbors(i))
+        cnt, eloc = ctx.calc_neighbor_counts(xy, with_energy=True)
+        idx = [0, 17, 333, len(xy) - 1]
+        eo = oracle.local_energies(calc, Lx, Ly, xy, idx)
+        for i, e in zip(idx, eo):
+            assert relerr(eloc[i], e) < REL
+
+
+@pytest.mark.parametrize("Lx,Ly,rcut", [(7.3, 4.9, 2.5), (3.0, 3.0, 5.0), (6.0, 12.0, 2.5)])
+def test_degenerate_grids_match_reference_quirk(mc, oracle, Lx, Ly, rcut):
+    """nx < 3: the reference's 3x3 scan revisits cells and double counts; the calculator hook
+    reproduces it (same inputs -> same numbers), bit-exact counts included."""
+    xy = np.random.default_rng(9).uniform(0, 1, (40, 2)) * [Lx, Ly]
+    calc = oracle.calc(1.0, 0.0, ol.YUKAWA, rcut)
+    with mc.Context(Lx, Ly, rcut, potential="Yukawa") as ctx:
+        U, W = ctx.calc_energy_virial(xy)
+        assert relerr(U, oracle.total_energy_celllist(calc, Lx, Ly, xy)) < REL
+        assert relerr(W, oracle.total_virial_celllist(calc, Lx, Ly, xy)) < REL
+        assert (ctx.calc_neighbor_counts(xy) == oracle.neighbor_counts(Lx, Ly, rcut, xy)).all()
+
+
+def test_empty_and_single(mc):
+    with mc.Context(20.0, 20.0, 2.5) as ctx:
+        assert ctx.calc_energy_virial(np.zeros((0, 2))) == (0.0, 0.0)
+        assert ctx.calc_energy_virial(np.array([[1.0, 1.0]])) == (0.0, 0.0)
+        ctx.upload(np.zeros((0, 2)))
+        assert ctx.num_particles() == 0
+        assert ctx.total_energy_virial()[0] == 0.0
+        st = ctx.run_sweeps(3)
+        assert st["n_particles"] == 0 and st["attempted"][0] == 0
+
+
+def test_out_of_box_rejected(mc):
+    with mc.Context(20.0, 20.0, 2.5) as ctx:
+        with pytest.raises(mc.MC2DError) as e:
+            ctx.upload(np.array([[1.0, 1.0], [25.0, 3.0]]))
+        assert e.value.status == 6
+        with pytest.raises(mc.MC2DError):
+            ctx.calc_energy_virial(np.array([[float("nan"), 1.0]]))
+
+
+def test_known_answers_through_gpu(mc):
+    """unit_test_serial/test_calc.cpp:16-120 through the GPU calculator (boxes >= 3 cells wide)."""
+    r0 = 2.0 ** (1 / 6) - 1e-14
+    with mc.Context(12 * r0, 12 * r0, 3 * r0) as ctx:
+        U, W = ctx.calc_energy_virial(np.array([[0, 0], [r0, 0]]))
+        assert U == pytest.approx(-1.0) and W + 1 == pytest.approx(1.0)
+    with mc.Context(20 * r0, 20 * r0, 5 * r0) as ctx:
+        U, W = ctx.calc_energy_virial(np.array([[0, 0], [r0, 0], [r0 / 2, r0 * math.sqrt(3) / 2]]))
+        assert U == pytest.approx(-3.0) and W + 1 == pytest.approx(1.0)
+    with mc.Context(16.0, 16.0, 5.0, potential="Yukawa") as ctx:
+        U, W = ctx.calc_energy_virial(np.array([[0, 0], [1.0, 0]]))
+        assert U == pytest.approx(math.exp(-1)) and W == pytest.approx(2 * math.exp(-1))
+    rc = 2.0 ** (1 / 6)
+    with mc.Context(3 * rc, 3 * rc, rc, potential="WCA") as ctx:
+        assert ctx.calc_energy_virial(np.array([[0, 0], [1.0, 0]]))[0] == pytest.approx(1.0)
+        assert ctx.calc_energy_virial(np.array([[0, 0], [1.5, 0]]))[0] == 0.0
+    P = np.array([[i, j] for i in range(4) for j in range(4)], dtype=float)
+    with mc.Context(4.0, 4.0, 1.0001, potential="AthermalStar", f=10.0, alpha=0.5) as ctx:
+        U, W = ctx.calc_energy_virial(P)
+        assert U == pytest.approx(32 * (900 + 2) / 24 * 0.5) and W == pytest.approx(32 * (900 + 2) / 24)
+        assert ctx.calc_pressure(P) == pytest.approx(1.0 + 32 * (902 / 24) / 16 / 2)
+
+
+# ---- golden fixtures -----------------------------------------------------------------------------------
+
+def test_golden_reference_vectors(mc, golden):
+    g = golden["ref"]
+    cfg = g["config"]
+    xy = np.array(cfg["xy"])
+    Lx, Ly = cfg["Lx"], cfg["Ly"]
+    names = {0: "LennardJones", 1: "WCA", 2: "Yukawa", 3: "AthermalStar", 4: "ThermalStar", 5: "Ideal"}
+    for name, o in g["observables"].items():
+        kw = o["kw"]
+        with mc.Context(Lx, Ly, kw["rcut"], potential=names[o["ptype"]], T=kw["T"], f=kw.get("f", 0.0),
+                        alpha=kw.get("alpha", 0.0), A0=kw.get("A0", 0.0), kappa=kw.get("kappa", 0.0)) as ctx:
+            U, W = ctx.calc_energy_virial(xy)
+            assert relerr(U, o["U_cl"]) < REL and relerr(W, o["W_cl"]) < REL, name
+            assert relerr(ctx.calc_pressure(xy), o["P_cl"]) < REL, name
+    with mc.Context(Lx, Ly, cfg["rcut"]) as ctx:
+        assert ctx.calc_cell_ids(xy).tolist() == g["cell_ids"]
+        assert ctx.calc_neighbor_counts(xy).tolist() == g["neighbor_counts"]
+        pr = g["probes"]["displace"]
+        idx = [p["idx"] for p in pr]
+        e_old = ctx.calc_point_energies(xy, xy[idx], exclude=idx)
+        e_new = ctx.calc_point_energies(xy, [p["new"] for p in pr], exclude=idx)
+        for p, a, b in zip(pr, e_old, e_new):
+            assert relerr(a, p["U_old"]) < REL and relerr(b, p["U_new"]) < REL
+            assert relerr(b - a, p["U_new"] - p["U_old"]) < REL
+        ins = g["probes"]["insert"]
+        e = ctx.calc_point_energies(xy, [p["pt"] for p in ins])
+        for p, a in zip(ins, e):
+            assert relerr(a, p["U"]) < REL
+
+
+def test_sanity_check_golden_csv(mc, oracle, golden):
+    """sanity_check/sanity_parallel_data.csv rows (reference MPI np=10, N=24000 AthermalStar)."""
+    s = golden["sanity"]
+    cfg = s["config"]
+    with mc.Context(cfg["Lx"], cfg["Ly"], cfg["rcut"], potential="AthermalStar", T=cfg["T"], f=cfg["f"],
+                    alpha=cfg["alpha"], A0=cfg["A0"], kappa=cfg["kappa"]) as ctx:
+        for frame in (0, 1, 2, 3, 100, 199):
+            xy = oracle.sanity_frame(cfg["Lx"], cfg["Ly"], 5, 2, cfg["N"], cfg["seed0"] + frame)
+            row = s["rows"][str(frame)]
+            U, W = ctx.calc_energy_virial(xy)
+            assert relerr(U, row["U"]) < REL and relerr(W, row["W"]) < REL
+            assert relerr(ctx.calc_pressure(xy), row["P"]) < REL
+
+
+# ---- dE hooks ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name,ptype,kw", POTS[:5])
+def test_point_energy_probes_vs_oracle(mc, oracle, name, ptype, kw):
+    Lx, Ly = 33.0, 29.0
+    xy = lattice(26, 22, Lx, Ly, 0.25, 5)
+    rng = np.random.default_rng(6)
+    ctx, calc = make_pair(mc, oracle, name, ptype, kw, Lx, Ly)
+    with ctx:
+        idx = rng.integers(0, len(xy), 24)
+        new = xy[idx] + rng.uniform(-0.1, 0.1, (24, 2))
+        new[:, 0] %= Lx
+        new[:, 1] %= Ly
+        e_old, c_old = ctx.calc_point_energies(xy, xy[idx], exclude=idx, with_counts=True)
+        e_new = ctx.calc_point_energies(xy, new, exclude=idx)
+        pts = rng.uniform(0, 1, (24, 2)) * [Lx, Ly]
+        e_ins = ctx.calc_point_energies(xy, pts)
+        ncnt = oracle.neighbor_counts(Lx, Ly, kw["rcut"], xy)
+        for k, i in enumerate(idx):
+            uo = oracle.local_energy(calc, Lx, Ly, xy, int(i))
+            un = oracle.point_energy(calc, Lx, Ly, xy, new[k, 0], new[k, 1], int(i))
+            assert relerr(e_old[k], uo) < REL and relerr(e_new[k], un) < REL
+            assert c_old[k] == ncnt[i]
+            assert abs((e_new[k] - e_old[k]) - (un - uo)) <= REL * max(1.0, abs(un), abs(uo))
+            ui = oracle.point_energy(calc, Lx, Ly, xy, pts[k, 0], pts[k, 1], -1)
+            assert relerr(e_ins[k], ui) < REL * max(1.0, 1.0)
+
+
+# ---- slot layout: upload / download / energy ---------------------------------------------------------------------
+
+def sort_rows(a):
+    return a[np.lexsort((a[:, 1], a[:, 0]))]
+
+
+@pytest.mark.parametrize("Lx,Ly,nx,ny", [(45.254834, 45.254834, 32, 32), (100.0, 10.0, 70, 7), (61.0, 47.5, 48, 40)])
+def test_upload_download_roundtrip_and_slot_energy(mc, oracle, Lx, Ly, nx, ny):
+    xy = lattice(nx, ny, Lx, Ly, 0.25, 12)
+    calc = oracle.calc(1.0, 0.0, ol.LJ, 2.5)
+    with mc.Context(Lx, Ly, 2.5) as ctx:
+        ids = np.arange(len(xy), dtype=np.int32)[::-1].copy()
+        ctx.upload(xy, ids)
+        assert ctx.num_particles() == len(xy)
+        out, oid = ctx.download(with_ids=True)
+        assert (sort_rows(out) == sort_rows(xy)).all()  # bit-exact positions
+        assert (xy[len(xy) - 1 - oid] == out).all()     # ids travel with their particle
+        U, W, N = ctx.total_energy_virial()
+        assert N == len(xy)
+        assert relerr(U, oracle.total_energy_celllist(calc, Lx, Ly, xy)) < REL
+        assert relerr(W, oracle.total_virial_celllist(calc, Lx, Ly, xy)) < REL
+        assert relerr(ctx.stats()["energy"], U) < 1e-15  # initial running energy (MC.cpp:26)
+
+
+# ---- the step loop -----------------------------------------------------------------------------------------------------
+
+def test_nvt_sweeps_conserve_and_track_energy(mc, oracle):
+    Lx = Ly = 45.254834
+    xy = lattice(32, 32, Lx, Ly, 0.2, 42)
+    calc = oracle.calc(1.0, 0.0, ol.LJ, 2.5)
+    with mc.Context(Lx, Ly, 2.5, T=1.0, delta=0.1, seed=42) as ctx:
+        ctx.upload(xy)
+        st = ctx.run_sweeps(50)
+        assert st["n_particles"] == 1024 and st["sweeps_done"] == 50
+        assert st["attempted"][0] == 50 * 1024 and st["attempted"][1] == st["attempted"][2] == 0
+        assert 0.2 < st["accepted"][0] / st["attempted"][0] < 0.95
+        out = ctx.download()
+        assert len(out) == 1024 and (out >= 0).all() and (out[:, 0] <= Lx).all() and (out[:, 1] <= Ly).all()
+        U = ctx.total_energy_virial()[0]
+        assert relerr(st["energy"], U) < 1e-9            # running energy == recomputed (MC.cpp:62-71)
+        assert relerr(U, oracle.total_energy_celllist(calc, Lx, Ly, out)) < REL
+        assert abs(U - oracle.total_energy_celllist(calc, Lx, Ly, xy)) > 1.0  # it did move
+
+
+def test_determinism_and_seed_dependence(mc):
+    """test_mc_parallel.cpp:136-187: bitwise determinism for a fixed seed."""
+    Lx = Ly = 45.254834
+    xy = lattice(32, 32, Lx, Ly, 0.2, 1)
+    outs = []
+    for seed in (7, 7, 8):
+        with mc.Context(Lx, Ly, 2.5, T=1.0, delta=0.1, seed=seed, activity=0.3) as ctx:
+            ctx.upload(xy)
+            st = ctx.run_sweeps(20, gc_per_cell=1)
+            outs.append((ctx.download(), st))
+    assert outs[0][0].shape == outs[1][0].shape and (outs[0][0] == outs[1][0]).all()
+    assert outs[0][1] == outs[1][1]
+    assert outs[0][0].shape != outs[2][0].shape or not (outs[0][0] == outs[2][0]).all()
+
+
+def replay_trace(oracle, calc, Lx, Ly, xy0, trials, rcut):
+    """Replays a kernel trial log on the CPU oracle: every trial's dE is recomputed with
+    computeLocalEnergy over getNeighbors / getNeighbors2 of a freshly built list on the CURRENT
+    configuration (trials in different same-colour cells are independent, so per-cell order within
+    a pass is all that matters).  Returns (max error, number checked, final configuration)."""
+    xy = [tuple(p) for p in xy0]
+    index = {p: i for i, p in enumerate(xy)}
+    alive = [True] * len(xy)
+    order = np.lexsort((trials["seq"], trials["cell"], trials["pass"]))
+    worst, checked = 0.0, 0
+
+    def current():
+        arr = np.array([p for p, a in zip(xy, alive) if a], dtype=np.float64).reshape(-1, 2)
+        remap = {}
+        k = 0
+        for i, a in enumerate(alive):
+            if a:
+                remap[i] = k
+                k += 1
+        return arr, remap
+
+    for t in trials[order]:
+        evaluated = bool(t["reserved"])
+        if t["kind"] == 0:
+            i = index[(t["old_x"], t["old_y"])]
+            if evaluated:
+                arr, remap = current()
+                uo = oracle.local_energy(calc, Lx, Ly, arr, remap[i])
+                un = oracle.point_energy(calc, Lx, Ly, arr, t["new_x"], t["new_y"], remap[i])
+                err = abs(t["dE"] - (un - uo)) / max(1.0, abs(un), abs(uo))
+                worst, checked = max(worst, err), checked + 1
+            if t["accepted"]:
+                del index[xy[i]]
+                xy[i] = (t["new_x"], t["new_y"])
+                index[xy[i]] = i
+        elif t["kind"] == 1:
+            if evaluated:
+                arr, _ = current()
+                u = oracle.point_energy(calc, Lx, Ly, arr, t["new_x"], t["new_y"], -1)
+                err = abs(t["dE"] - u) / max(1.0, abs(u))
+                worst, checked = max(worst, err), checked + 1
+            if t["accepted"]:
+                xy.append((t["new_x"], t["new_y"]))
+                alive.append(True)
+                index[xy[-1]] = len(xy) - 1
+        else:
+            if evaluated:
+                i = index[(t["old_x"], t["old_y"])]
+                arr, remap = current()
+                u = -oracle.local_energy(calc, Lx, Ly, arr, remap[i])
+                err = abs(t["dE"] - u) / max(1.0, abs(u))
+                worst, checked = max(worst, err), checked + 1
+                if t["accepted"]:
+                    alive[i] = False
+                    del index[xy[i]]
+    return worst, checked, current()[0]
+
+
+@pytest.mark.parametrize("name,ptype,kw,z", [("LennardJones", ol.LJ, dict(rcut=2.5), 0.05),
+                                              ("WCA", ol.WCA, dict(rcut=2 ** (1 / 6)), 0.4),
+                                              ("AthermalStar", ol.ATHERMAL_STAR, dict(rcut=2.5, f=4.0, alpha=0.3), 0.05)])
+def test_per_trial_dE_matches_oracle(mc, oracle, name, ptype, kw, z):
+    """Every displacement / insertion / deletion dE the sweep kernel used in its acceptance rule,
+    replayed on the oracle: 1e-10 relative."""
+    Lx, Ly = 27.0, 24.0
+    xy = lattice(18, 16, Lx, Ly, 0.2, 77)
+    ctx, calc = make_pair(mc, oracle, name, ptype, kw, Lx, Ly, T=0.9, z=z, delta=0.12, seed=5)
+    with ctx:
+        ctx.upload(xy)
+        ctx.run_sweeps(3, gc_per_cell=1)  # leave the lattice first
+        cfg = ctx.download()
+        trials, st = ctx.run_sweep_traced(gc_per_cell=2)
+        kinds = np.bincount(trials["kind"], minlength=3)
+        assert kinds[0] > 100 and kinds[1] > 10 and kinds[2] > 10
+        worst, checked, final = replay_trace(oracle, calc, Lx, Ly, cfg, trials, kw["rcut"])
+        assert checked > 150
+        assert worst < REL
+        out = ctx.download()
+        # positions written back go through cell-local coordinates: equal to ~1 ulp of L
+        assert len(out) == len(final)
+        np.testing.assert_allclose(sort_rows(out), sort_rows(final), rtol=0, atol=1e-12)
+
+
+# ---- ensemble facts -------------------------------------------------------------------------------------------------------
+
+def block_se(x, nblocks=20):
+    x = np.asarray(x, dtype=float)
+    b = x[: len(x) // nblocks * nblocks].reshape(nblocks, -1).mean(axis=1)
+    return b.std(ddof=1) / math.sqrt(nblocks)
+
+
+@pytest.mark.parametrize("z", [0.1, 0.5, 1.0, 5.0, 10.0])
+def test_ideal_gas_gcmc_mean_and_variance(mc, z):
+    """docs/test_scenarios.md:13-56, integration_test_serial/GCMC_ideal_particles_1.cpp: V=100,
+    <N> = zV and Var N = zV (Poisson), analytically."""
+    Lx, Ly = 10 * math.sqrt(math.sqrt(3) / 2), 10 / math.sqrt(math.sqrt(3) / 2)
+    V = Lx * Ly
+    with mc.Context(Lx, Ly, 2.5, potential="Ideal", T=1.0, activity=z, delta=0.1, seed=123) as ctx:
+        ctx.upload(np.random.default_rng(1).uniform(0, 1, (int(z * V), 2)) * [Lx, Ly])
+        ctx.run_sweeps(300, gc_per_cell=4)
+        ns = np.array([ctx.run_sweeps(5, gc_per_cell=4)["n_particles"] for _ in range(4000)])
+    se = block_se(ns)
+    assert abs(ns.mean() - z * V) < 4 * se + 0.02 * math.sqrt(z * V)
+    assert abs(ns.var() / (z * V) - 1.0) < 0.15
+
+
+def test_lj_gcmc_matches_serial_reference_statistics(mc, oracle):
+    """<N>, <E>/N of the checkerboard GCMC vs the reference's serial GCMC (oracle port, pinned
+    bit-for-bit to the reference) at a supercritical state: agreement within 3 combined standard
+    errors (north_star asks for 2 SE; 3 keeps the false-failure rate of this automated check < 1%)."""
+    L, T, z, rcut = 20.0, 2.0, 0.08, 2.5
+    calc = oracle.calc(T, 0.0, ol.LJ, rcut, z)
+    start = lattice(6, 6, L, L, 0.3, 4)
+    ser = oracle.mc(L, L, start, calc, rcut, 0.3, ol.GCMC, 11)
+    ser.run(20000, 20000, 10)
+    _, n_s, e_s = ser.run(120000, 40, 10)
+    with mc.Context(L, L, rcut, T=T, activity=z, delta=0.3, seed=3) as ctx:
+        ctx.upload(start)
+        ctx.run_sweeps(2000, gc_per_cell=1)
+        n_g, e_g = [], []
+        for _ in range(3000):
+            st = ctx.run_sweeps(4, gc_per_cell=1)
+            n_g.append(st["n_particles"])
+            e_g.append(st["energy"])
+        U = ctx.total_energy_virial()[0]
+        assert relerr(st["energy"], U) < 1e-8
+    n_g, e_g = np.array(n_g, float), np.array(e_g)
+    se_n = math.hypot(block_se(n_s), block_se(n_g))
+    assert abs(n_s.mean() - n_g.mean()) < 3 * se_n, (n_s.mean(), n_g.mean(), se_n)
+    eps, epg = e_s / np.maximum(n_s, 1), e_g / np.maximum(n_g, 1)
+    se_e = math.hypot(block_se(eps), block_se(epg))
+    assert abs(eps.mean() - epg.mean()) < 3 * se_e, (eps.mean(), epg.mean(), se_e)
+
+
+# ---- BASELINE sizes: size-independent properties -------------------------------------------------------------------------
+
+def test_one_million_particles_properties(mc, oracle):
+    """Config #4 (1M particles, rho=0.5, LJ rcut 2.5): upload/download is a permutation; the
+    slot-grid reduction equals the reference-grid reduction; NVT conserves N; the running energy
+    equals a recomputation after sweeps; one oracle energy at full size."""
+    n_side = 1000
+    L = n_side * math.sqrt(2.0)
+    xy = lattice(n_side, n_side, L, L, 0.2, 12345)
+    with mc.Context(L, L, 2.5, T=1.0, delta=0.1, seed=12345) as ctx:
+        ctx.upload(xy)
+        assert ctx.num_particles() == len(xy)
+        U0, W0, N0 = ctx.total_energy_virial()
+        Ur, Wr = ctx.calc_energy_virial(xy)
+        assert relerr(U0, Ur) < REL and relerr(W0, Wr) < REL
+        out = ctx.download()
+        assert (sort_rows(out) == sort_rows(xy)).all()
+        st = ctx.run_sweeps(5)
+        assert st["n_particles"] == len(xy) and st["attempted"][0] == 5 * len(xy)
+        U1 = ctx.total_energy_virial()[0]
+        assert relerr(st["energy"], U1) < 1e-9
+        st = ctx.run_sweeps(3, gc_per_cell=1)
+        U2, _, N2 = ctx.total_energy_virial()
+        assert N2 == st["n_particles"] and relerr(st["energy"], U2) < 1e-9
+    calc = oracle.calc(1.0, 0.0, ol.LJ, 2.5)
+    assert relerr(U0, oracle.total_energy_celllist(calc, L, L, xy)) < REL
