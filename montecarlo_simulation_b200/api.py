@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libmc2d.so")
+LIB_PATH = os.environ.get("MC2D_LIB", os.path.join(PKG, "libmc2d.so"))  # MC2D_LIB: tuning builds
 
 LENNARD_JONES, WCA, YUKAWA, ATHERMAL_STAR, THERMAL_STAR, IDEAL = range(6)
 POTENTIAL_NAMES = {"LennardJones": 0, "WCA": 1, "Yukawa": 2, "AthermalStar": 3, "ThermalStar": 4, "Ideal": 5}

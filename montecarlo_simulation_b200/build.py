@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmc2d.so")
 SOURCES = ["mc2d.cu"]
-HEADERS = ["mc2d_kernels.cuh", "pair_potentials.cuh", "philox.h", os.path.join("..", "..", "include", "mc2d.h")]
+HEADERS = ["mc2d_kernels.cuh", "sweep_kernel.cuh", "pair_potentials.cuh", "philox.h", os.path.join("..", "..", "include", "mc2d.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -44,7 +44,8 @@ def needs_build() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(PKG, "..", "include"), "-o", LIB] + \
+    extra = os.environ.get("MC2D_NVCC_EXTRA", "").split()  # e.g. -DMC2D_SWEEP_MIN_BLOCKS=4 for tuning
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-I", os.path.join(PKG, "..", "include"), "-o", LIB] + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr

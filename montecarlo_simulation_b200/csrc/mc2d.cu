@@ -292,6 +292,8 @@ extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
     g.ncs = g.ncol + 2 * g.ghost;
     g.K = 0;
     g.Lx = p->Lx;
+    g.inv_dx = 1.0 / g.dx;
+    g.inv_dy = 1.0 / g.dy;
     g.Ly = p->Ly;
     g.ox = g.oy = 0.0;
     CU(cudaSetDevice(ctx->dev));
@@ -620,8 +622,8 @@ static int launch_energy(mc2d_ctx *ctx, const V &view, int ncells, int half, boo
                 view, ctx->pp, ctx->r2cut, half, pU, pW, ctx->d_pair_stats, nullptr, nullptr);
     });
     const double scale = half ? 1.0 : 0.5;  // directed double count is halved (thermodynamic_calculator.cpp:211,232)
-    k_reduce_partials<<<1, 256, 0, ctx->stream>>>(pU, nblocks, scale, ctx->d_energy + 1, 0);
-    k_reduce_partials<<<1, 256, 0, ctx->stream>>>(pW, nblocks, scale, ctx->d_energy + 2, 0);
+    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(pU, nblocks, scale, ctx->d_energy + 1, 0);
+    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(pW, nblocks, scale, ctx->d_energy + 2, 0);
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 3;
     double uw[2];
@@ -836,6 +838,8 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     const int nact = (g.ncol / 2) * (g.ny / 2);
     const int nblocks = std::max(1, (nact + wpb - 1) / wpb);
     CU(ctx->partial.ensure(sizeof(double) * 4 * (size_t)nblocks));
+    // per-CTA dU accumulators live across the whole batch and are reduced once at its end
+    CU(cudaMemsetAsync(ctx->partial.p, 0, sizeof(double) * 4 * (size_t)nblocks, ctx->stream));
     if (trace) {
         CU(ctx->trace_buf.ensure(sizeof(mc2d_trial) * (size_t)trace_cap));
         CU(cudaMemsetAsync(ctx->d_trace_n, 0, sizeof(unsigned long long), ctx->stream));
@@ -914,10 +918,10 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
                 if (rc) return rc;
             }
         }
-        k_reduce_partials<<<1, 256, 0, ctx->stream>>>(ctx->partial.as<double>(), 4 * nblocks, 1.0, ctx->d_energy, 1);
-        ctx->launches++;
         ctx->sweep++;
     }
+    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(ctx->partial.as<double>(), 4 * nblocks, 1.0, ctx->d_energy, 1);
+    ctx->launches++;
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     int errv[4];
     CU(cudaMemcpyAsync(errv, ctx->d_err, sizeof errv, cudaMemcpyDeviceToHost, ctx->stream));

@@ -27,6 +27,7 @@ struct Grid {
     int ncs;         // stored columns = ncol + 2*ghost
     int K;           // slots per cell
     double dx, dy, Lx, Ly;
+    double inv_dx, inv_dy;
     double ox, oy;   // grid origin shift of the current sweep, in [0,dx) x [0,dy)
 };
 
@@ -176,7 +177,40 @@ __global__ void __launch_bounds__(256) k_energy_virial(V v, PairParams pp, doubl
                 tb[c] = __shfl_sync(FULL_MASK, nb_b, c);
                 ts[c] = __shfl_sync(FULL_MASK, excl, c);
             }
-            for (int i = 0; i < n0; ++i) {
+            if (!PERP) {
+                // production order: every lane decodes and loads ITS candidate once per chunk, the
+                // cell's own particles are the inner loop (uniform, L1-broadcast loads)
+                for (int k = lane; k < M; k += 32) {
+                    int c = 0;
+#pragma unroll
+                    for (int q = 1; q < 9; ++q)
+                        if (k >= ts[q]) c = q;
+                    int cb = tb[0], cs = ts[0];
+#pragma unroll
+                    for (int q = 1; q < 9; ++q)
+                        if (c == q) { cb = tb[q]; cs = ts[q]; }
+                    const int j = cb + (k - cs);
+                    const bool same_cell = (cb == b0);
+                    const double2 pj = v.pos[j];
+                    // own particles i that pair with candidate j: all of them, except in the own
+                    // cell where half keeps i < j and full keeps i != j
+                    const int jrel = j - b0;
+                    for (int i = 0; i < n0; ++i) {
+                        if (same_cell && (half ? (jrel <= i) : (jrel == i))) continue;
+                        const double2 pi = v.pos[b0 + i];
+                        const double r2 = exact_r2(pi.x, pi.y, pj.x, pj.y, v_Lx(v), v_Ly(v), hLx, hLy);
+                        ++tests;
+                        if (r2 <= r2cut) {  // inclusive, cell_list.cpp:62
+                            double u, wv;
+                            pair_uw<POT>(r2, pp, u, wv);
+                            accU += u;
+                            accW += wv;
+                            ++evals;
+                        }
+                    }
+                }
+            }
+            for (int i = 0; PERP && i < n0; ++i) {
                 const double2 pi = v.pos[b0 + i];
                 double ui = 0.0, wi = 0.0;
                 int ci = 0;
@@ -234,11 +268,20 @@ __global__ void __launch_bounds__(256) k_energy_virial(V v, PairParams pp, doubl
 }
 
 // fixed-order final reduction of per-CTA partials: out[0] += / = scale * sum(part[0..n))
-__global__ void __launch_bounds__(256) k_reduce_partials(const double *part, int n, double scale, double *out,
-                                                         int accumulate) {
+__global__ void __launch_bounds__(1024) k_reduce_partials(const double *part, int n, double scale, double *out,
+                                                          int accumulate) {
     __shared__ double red[32];
-    double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // 4 independent chains: loads overlap
+    int i = threadIdx.x;
+    const int st = blockDim.x;
+    for (; i + 3 * st < n; i += 4 * st) {
+        s0 += part[i];
+        s1 += part[i + st];
+        s2 += part[i + 2 * st];
+        s3 += part[i + 3 * st];
+    }
+    for (; i < n; i += st) s0 += part[i];
+    double s = (s0 + s1) + (s2 + s3);
     s = block_sum(s, red);
     if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.0) + scale * s;
 }
@@ -292,10 +335,17 @@ __global__ void __launch_bounds__(256) k_point_energy(CsrView v, PairParams pp, 
 // rank's slab get the sentinel key `sentinel` and sort to the end.
 // flags[0] |= 1 when a coordinate is NaN or outside [0,L].
 // ---------------------------------------------------------------------------------------------
+// Canonical cell of a position on the (shifted) checkerboard grid.  A function of the particle
+// alone, so every particle belongs to exactly one cell whatever the rounding; multiplication by
+// the reciprocal and a conditional wrap instead of division and modulo (x - ox lies in (-dx, Lx],
+// so the raw index lies in [-1, nx]).  Not a parity hook: the reference grid uses the exact
+// division of cell_list.cpp:103-109 (k_cell_keys mode 0).
 __device__ __forceinline__ void sweep_cell_of(const Grid &g, double x, double y, int &gcx, int &cy) {
-    int ix = (int)floor((x - g.ox) / g.dx), iy = (int)floor((y - g.oy) / g.dy);
-    gcx = wrap_index(ix, g.nx);
-    cy = wrap_index(iy, g.ny);
+    int ix = (int)floor((x - g.ox) * g.inv_dx), iy = (int)floor((y - g.oy) * g.inv_dy);
+    if (ix < 0) ix += g.nx; else if (ix >= g.nx) ix -= g.nx;
+    if (iy < 0) iy += g.ny; else if (iy >= g.ny) iy -= g.ny;
+    gcx = ix;
+    cy = iy;
 }
 
 __global__ void k_cell_keys(const double2 *pos, int n, int mode, int nx, int ny, double cdx, double cdy, double Lx,
@@ -385,36 +435,61 @@ __global__ void __launch_bounds__(256) k_rebin(const double2 *pos_o, const int *
     const int gcx = gn.col0 + (lcx - gn.ghost);
     const int K = gn.K;
     const size_t obase = (size_t)(lcx * gn.ny + cy) * K;
-    int nout = 0;
-    for (int ddx = -1; ddx <= 1; ++ddx) {
-        if (gn.nx == 2 && ddx < 0) continue;
-        const int ocx = gn.ghost ? lcx + ddx : (lcx + ddx + gn.nx) % gn.nx;
-        for (int ddy = -1; ddy <= 1; ++ddy) {
-            if (gn.ny == 2 && ddy < 0) continue;
+    // the 3x3 old cells, flattened into one candidate list (lane k <-> k-th old particle)
+    int oc_cell = 0, oc_n = 0;
+    if (lane < 9) {
+        const int ddx = lane / 3 - 1, ddy = lane % 3 - 1;
+        if (!((gn.nx == 2 && ddx < 0) || (gn.ny == 2 && ddy < 0))) {
+            const int ocx = gn.ghost ? lcx + ddx : (lcx + ddx + gn.nx) % gn.nx;
             const int ocy = (cy + ddy + gn.ny) % gn.ny;
-            const int oc = ocx * gn.ny + ocy;
-            const int n = cnt_o[oc];
-            for (int s0 = 0; s0 < n; s0 += 32) {
-                const int s = s0 + lane;
-                bool take = false;
-                double2 p = make_double2(0.0, 0.0);
-                if (s < n) {
-                    p = pos_o[(size_t)oc * K + s];
-                    int ngx, ncy;
-                    sweep_cell_of(gn, p.x, p.y, ngx, ncy);
-                    take = (ngx == gcx && ncy == cy);
-                }
-                const unsigned m = __ballot_sync(FULL_MASK, take);
-                if (take) {
-                    const int off = nout + __popc(m & ((1u << lane) - 1u));
-                    if (off < K) {
-                        pos_n[obase + off] = p;
-                        if (ids_n) ids_n[obase + off] = ids_o[(size_t)oc * K + s];
-                    }
-                }
-                nout += __popc(m);
+            oc_cell = ocx * gn.ny + ocy;
+            oc_n = cnt_o[oc_cell];
+        }
+    }
+    int incl = oc_n;
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+        int t = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const int M = __shfl_sync(FULL_MASK, incl, 8);
+    const int excl = incl - oc_n;
+    int tc[9], ts[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        tc[c] = __shfl_sync(FULL_MASK, oc_cell, c);
+        ts[c] = __shfl_sync(FULL_MASK, excl, c);
+    }
+    int nout = 0;
+    for (int k0 = 0; k0 < M; k0 += 32) {
+        const int k = k0 + lane;
+        bool take = false;
+        double2 p = make_double2(0.0, 0.0);
+        size_t src = 0;
+        if (k < M) {
+            int c = 0;
+#pragma unroll
+            for (int q = 1; q < 9; ++q)
+                if (k >= ts[q]) c = q;
+            int cc = tc[0], cs = ts[0];
+#pragma unroll
+            for (int q = 1; q < 9; ++q)
+                if (c == q) { cc = tc[q]; cs = ts[q]; }
+            src = (size_t)cc * K + (k - cs);
+            p = pos_o[src];
+            int ngx, ncy;
+            sweep_cell_of(gn, p.x, p.y, ngx, ncy);
+            take = (ngx == gcx && ncy == cy);
+        }
+        const unsigned m = __ballot_sync(FULL_MASK, take);
+        if (take) {
+            const int off = nout + __popc(m & ((1u << lane) - 1u));
+            if (off < K) {
+                pos_n[obase + off] = p;
+                if (ids_n) ids_n[obase + off] = ids_o[src];
             }
         }
+        nout += __popc(m);
     }
     if (lane == 0) {
         cnt_n[lcx * gn.ny + cy] = min(nout, K);
@@ -442,339 +517,5 @@ __global__ void k_sum_counts(const int *cnt, int cell0, int ncell, unsigned long
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, (unsigned long long)n);
 }
 
-// ---------------------------------------------------------------------------------------------
-// K2 + K3 — one colour pass of the checkerboard sweep: trial displacements and GCMC
-// insert/delete trials for every cell of one colour.
-//   replaces displacementMove_cell_list_dE (MC.cpp:96-123), grandCanonicalMove (MC.cpp:189-249),
-//   getNeighbors/getNeighbors2 (cell_list.cpp:43-101) and, on the MPI side, do_one_parity_step_ /
-//   try_displacement_ / local_energy_of_* (MC_parallel.cpp:117-216).
-//
-// One warp per active cell.  The 8 surrounding cells (frozen during the pass: same-colour cells
-// are >= one cell >= rcut apart) are staged once into shared memory as coordinates LOCAL to the
-// active cell (periodic image already applied, so the inner loop has no minimum-image code); the
-// cell's own particles live in shared memory and are updated in place.  Each trial: one Philox
-// call (stream = global cell id), lanes evaluate pair energies for old and new position against
-// their candidates, warp-shuffle reduction gives dE, every lane takes the same Metropolis
-// decision.  Detailed balance: a displacement that leaves the cell is rejected; insertions are
-// uniform in the cell with acceptance z*A_cell/(n+1)*exp(-beta dU), deletions n/(z*A_cell)*exp(-beta dU)
-// (the per-cell form of MC.cpp:201,226).
-// MINIMG = true adds a per-pair minimum image (grids with fewer than 4 cells across).
-// ---------------------------------------------------------------------------------------------
-struct SweepArgs {
-    double2 *pos;
-    int *cnt;
-    int *ids;
-    Grid g;
-    PairParams pp;
-    double r2cut, beta, zA, delta;
-    int colour, pass;
-    uint32_t sweep_lo, sweep_hi, seed_lo, seed_hi;
-    int disp_mult, n_gc;
-    double p_ins, p_del;
-    double *partial_dU;            // one per CTA
-    unsigned long long *counters;  // [0..2] attempted, [3..5] accepted, [6] overflow
-    mc2d_trial *trace;
-    unsigned long long *trace_n;
-    long long trace_cap;
-};
 
-template <int POT>
-__device__ __forceinline__ double pair_e_cut(double dx, double dy, double r2cut, const PairParams &pp) {
-    const double r2 = dx * dx + dy * dy;
-    return (r2 <= r2cut) ? pair_u<POT>(r2, pp) : 0.0;
-}
-
-template <int POT, bool MINIMG, bool TRACE>
-__global__ void __launch_bounds__(256) k_sweep(SweepArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double red[32];
-    __shared__ unsigned int cred[8][7];
-    const Grid &g = a.g;
-    const int K = g.K;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int w = blockIdx.x * wpb + wib;
-    // per-warp shared memory: own[K] double2, own_id[K] int (if ids), nb[8K] double2
-    const int nb_cap = (POT == POT_IDEAL) ? 0 : 8 * K;
-    const size_t per_warp = (size_t)(K + nb_cap) * sizeof(double2) + (size_t)K * sizeof(int);
-    double2 *own = reinterpret_cast<double2 *>(smem_raw + wib * per_warp);
-    double2 *nb = own + K;
-    int *own_id = reinterpret_cast<int *>(nb + nb_cap);
-
-    const int nay = g.ny >> 1;
-    const int nact = (g.ncol >> 1) * nay;
-    double dU_total = 0.0;
-    unsigned int c_att[3] = {0, 0, 0}, c_acc[3] = {0, 0, 0}, c_ovf = 0;
-
-    if (w < nact) {
-        const int px = a.colour & 1, py = a.colour >> 1;
-        const int acx = w / nay, acy = w % nay;
-        const int lcx = g.ghost + 2 * acx + px;  // stored column (col0 is even, so parity is global)
-        const int cy = 2 * acy + py;
-        const int gcx = g.col0 + 2 * acx + px;
-        const int cell = lcx * g.ny + cy;
-        const uint32_t cell_gid = (uint32_t)(gcx * g.ny + cy);
-        const double x_lo = g.ox + gcx * g.dx, y_lo = g.oy + cy * g.dy;
-        const double hLx = 0.5 * g.Lx, hLy = 0.5 * g.Ly;
-        int n_own = a.cnt[cell];
-        const int n_disp = a.disp_mult * n_own;
-        if (n_disp > 0 || a.n_gc > 0) {
-            // ---- stage the own cell (local coordinates) ----
-            for (int s = lane; s < n_own; s += 32) {
-                double2 p = a.pos[(size_t)cell * K + s];
-                double ux = p.x - x_lo, uy = p.y - y_lo;
-                if (ux < -hLx) ux += g.Lx; else if (ux >= hLx) ux -= g.Lx;
-                if (uy < -hLy) uy += g.Ly; else if (uy >= hLy) uy -= g.Ly;
-                own[s] = make_double2(ux, uy);
-                if (a.ids) own_id[s] = a.ids[(size_t)cell * K + s];
-            }
-            // ---- stage the 8 neighbour cells, flattened ----
-            int M = 0;
-            if (POT != POT_IDEAL) {
-                int nb_cell = -1, nb_n = 0;
-                if (lane < 8) {
-                    const int o = lane + (lane >= 4);  // skip (0,0)
-                    const int ddx = o / 3 - 1, ddy = o % 3 - 1;
-                    const bool dup = (g.nx == 2 && ddx < 0) || (g.ny == 2 && ddy < 0);
-                    if (!dup) {
-                        const int ncx = g.ghost ? lcx + ddx : (lcx + ddx + g.nx) % g.nx;
-                        const int ncy = (cy + ddy + g.ny) % g.ny;
-                        nb_cell = ncx * g.ny + ncy;
-                        if (nb_cell != cell) nb_n = a.cnt[nb_cell];
-                    }
-                }
-                int incl = nb_n;
-#pragma unroll
-                for (int d = 1; d < 8; d <<= 1) {
-                    int t = __shfl_up_sync(FULL_MASK, incl, d);
-                    if (lane >= d) incl += t;
-                }
-                M = __shfl_sync(FULL_MASK, incl, 7);
-                const int excl = incl - nb_n;
-                int tc[8], ts[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    tc[c] = __shfl_sync(FULL_MASK, nb_cell, c);
-                    ts[c] = __shfl_sync(FULL_MASK, excl, c);
-                }
-                for (int k = lane; k < M; k += 32) {
-                    int c = 0;
-#pragma unroll
-                    for (int q = 1; q < 8; ++q)
-                        if (k >= ts[q]) c = q;
-                    int cc = tc[0], cs = ts[0];
-#pragma unroll
-                    for (int q = 1; q < 8; ++q)
-                        if (c == q) { cc = tc[q]; cs = ts[q]; }
-                    double2 p = a.pos[(size_t)cc * K + (k - cs)];
-                    double ux = p.x - x_lo, uy = p.y - y_lo;
-                    if (ux < -hLx) ux += g.Lx; else if (ux >= hLx) ux -= g.Lx;
-                    if (uy < -hLy) uy += g.Ly; else if (uy >= hLy) uy -= g.Ly;
-                    nb[k] = make_double2(ux, uy);
-                }
-            }
-            __syncwarp();
-            bool dirty = false;
-
-            // ---- K2: displacement trials (MC.cpp:96-123) ----
-            for (int t = 0; t < n_disp; ++t) {
-                const Philox4 r = philox4x32_10(cell_gid, MC2D_TAG_DISP | (uint32_t)t, a.sweep_lo, a.sweep_hi,
-                                                a.seed_lo, a.seed_hi);
-                const int i = (int)__umulhi(r.x, (uint32_t)n_own);
-                const double2 uo = own[i];
-                double2 un;
-                un.x = uo.x + a.delta * (2.0 * mc2d_u01(r.y) - 1.0);
-                un.y = uo.y + a.delta * (2.0 * mc2d_u01(r.z) - 1.0);
-                ++c_att[0];
-                const bool inside = (un.x >= 0.0 && un.x < g.dx && un.y >= 0.0 && un.y < g.dy);
-                double dE = 0.0;
-                bool accept = false;
-                if (inside) {
-                    if (POT != POT_IDEAL) {
-                        double acc = 0.0;
-                        for (int k = lane; k < M; k += 32) {
-                            const double2 c = nb[k];
-                            double dxn = c.x - un.x, dyn = c.y - un.y, dxo = c.x - uo.x, dyo = c.y - uo.y;
-                            if (MINIMG) {
-                                if (dxn >= hLx) dxn -= g.Lx; else if (dxn < -hLx) dxn += g.Lx;
-                                if (dyn >= hLy) dyn -= g.Ly; else if (dyn < -hLy) dyn += g.Ly;
-                                if (dxo >= hLx) dxo -= g.Lx; else if (dxo < -hLx) dxo += g.Lx;
-                                if (dyo >= hLy) dyo -= g.Ly; else if (dyo < -hLy) dyo += g.Ly;
-                            }
-                            acc += pair_e_cut<POT>(dxn, dyn, a.r2cut, a.pp) - pair_e_cut<POT>(dxo, dyo, a.r2cut, a.pp);
-                        }
-                        for (int s = lane; s < n_own; s += 32) {
-                            if (s == i) continue;
-                            const double2 c = own[s];
-                            acc += pair_e_cut<POT>(c.x - un.x, c.y - un.y, a.r2cut, a.pp) -
-                                   pair_e_cut<POT>(c.x - uo.x, c.y - uo.y, a.r2cut, a.pp);
-                        }
-                        dE = warp_sum(acc);
-                    }
-                    accept = (dE <= 0.0) || (mc2d_u01(r.w) < exp(-a.beta * dE));  // MC.cpp:110-115
-                    if (accept) {
-                        __syncwarp();
-                        if (lane == 0) own[i] = un;
-                        dU_total += dE;
-                        ++c_acc[0];
-                        dirty = true;
-                    }
-                }
-                if (TRACE && lane == 0) {
-                    unsigned long long slot = atomicAdd(a.trace_n, 1ull);
-                    if ((long long)slot < a.trace_cap) {
-                        mc2d_trial tr;
-                        tr.pass = a.pass; tr.cell = (int)cell_gid; tr.seq = t; tr.kind = 0;
-                        tr.accepted = accept ? 1 : 0; tr.reserved = inside ? 1 : 0;
-                        double ox_ = x_lo + uo.x, oy_ = y_lo + uo.y, nx_ = x_lo + un.x, ny_ = y_lo + un.y;
-                        if (ox_ >= g.Lx) ox_ -= g.Lx; if (oy_ >= g.Ly) oy_ -= g.Ly;
-                        if (nx_ >= g.Lx) nx_ -= g.Lx; if (ny_ >= g.Ly) ny_ -= g.Ly;
-                        tr.old_x = ox_; tr.old_y = oy_; tr.new_x = nx_; tr.new_y = ny_;
-                        tr.dE = inside ? dE : nan("");
-                        a.trace[slot] = tr;
-                    }
-                }
-                __syncwarp();
-            }
-
-            // ---- K3: grand-canonical trials (MC.cpp:189-249), restricted to the active cell ----
-            for (int t = 0; t < a.n_gc; ++t) {
-                const Philox4 r = philox4x32_10(cell_gid, MC2D_TAG_GC | (uint32_t)t, a.sweep_lo, a.sweep_hi,
-                                                a.seed_lo, a.seed_hi);
-                const double sel = mc2d_u01(r.x);
-                int kind = -1;
-                bool accept = false, evaluated = false;
-                double dE = 0.0;
-                double2 pt = make_double2(0.0, 0.0), old = make_double2(0.0, 0.0);
-                if (sel < a.p_ins) {  // insertion
-                    kind = 1;
-                    ++c_att[1];
-                    pt.x = mc2d_u01(r.y) * g.dx;
-                    pt.y = mc2d_u01(r.z) * g.dy;
-                    if (pt.x >= g.dx) pt.x = 0.0;
-                    if (pt.y >= g.dy) pt.y = 0.0;
-                    if (n_own >= K) {
-                        ++c_ovf;
-                    } else {
-                        if (POT != POT_IDEAL) {
-                            double acc = 0.0;
-                            for (int k = lane; k < M; k += 32) {
-                                const double2 c = nb[k];
-                                double dxn = c.x - pt.x, dyn = c.y - pt.y;
-                                if (MINIMG) {
-                                    if (dxn >= hLx) dxn -= g.Lx; else if (dxn < -hLx) dxn += g.Lx;
-                                    if (dyn >= hLy) dyn -= g.Ly; else if (dyn < -hLy) dyn += g.Ly;
-                                }
-                                acc += pair_e_cut<POT>(dxn, dyn, a.r2cut, a.pp);
-                            }
-                            for (int s = lane; s < n_own; s += 32) {
-                                const double2 c = own[s];
-                                acc += pair_e_cut<POT>(c.x - pt.x, c.y - pt.y, a.r2cut, a.pp);
-                            }
-                            dE = warp_sum(acc);
-                        }
-                        evaluated = true;
-                        const double av = a.zA / (double)(n_own + 1) * exp(-a.beta * dE);  // MC.cpp:201
-                        accept = (av >= 1.0) || (mc2d_u01(r.w) < av);
-                        if (accept) {
-                            __syncwarp();
-                            if (lane == 0) {
-                                own[n_own] = pt;
-                                if (a.ids) own_id[n_own] = -1;
-                            }
-                            ++n_own;
-                            dU_total += dE;
-                            ++c_acc[1];
-                            dirty = true;
-                        }
-                    }
-                } else if (sel < a.p_ins + a.p_del) {  // deletion
-                    kind = 2;
-                    ++c_att[2];
-                    if (n_own > 0) {
-                        const int i = (int)__umulhi(r.y, (uint32_t)n_own);
-                        old = own[i];
-                        if (POT != POT_IDEAL) {
-                            double acc = 0.0;
-                            for (int k = lane; k < M; k += 32) {
-                                const double2 c = nb[k];
-                                double dxo = c.x - old.x, dyo = c.y - old.y;
-                                if (MINIMG) {
-                                    if (dxo >= hLx) dxo -= g.Lx; else if (dxo < -hLx) dxo += g.Lx;
-                                    if (dyo >= hLy) dyo -= g.Ly; else if (dyo < -hLy) dyo += g.Ly;
-                                }
-                                acc += pair_e_cut<POT>(dxo, dyo, a.r2cut, a.pp);
-                            }
-                            for (int s = lane; s < n_own; s += 32) {
-                                if (s == i) continue;
-                                const double2 c = own[s];
-                                acc += pair_e_cut<POT>(c.x - old.x, c.y - old.y, a.r2cut, a.pp);
-                            }
-                            dE = -warp_sum(acc);  // MC.cpp:225
-                        }
-                        evaluated = true;
-                        const double av = (double)n_own / a.zA * exp(-a.beta * dE);  // MC.cpp:226
-                        accept = (av >= 1.0) || (mc2d_u01(r.w) < av);
-                        if (accept) {
-                            __syncwarp();
-                            if (lane == 0) {
-                                own[i] = own[n_own - 1];
-                                if (a.ids) own_id[i] = own_id[n_own - 1];
-                            }
-                            --n_own;
-                            dU_total += dE;
-                            ++c_acc[2];
-                            dirty = true;
-                        }
-                    }
-                }
-                if (TRACE && lane == 0 && kind > 0) {
-                    unsigned long long slot = atomicAdd(a.trace_n, 1ull);
-                    if ((long long)slot < a.trace_cap) {
-                        mc2d_trial tr;
-                        tr.pass = a.pass; tr.cell = (int)cell_gid; tr.seq = n_disp + t; tr.kind = kind;
-                        tr.accepted = accept ? 1 : 0; tr.reserved = evaluated ? 1 : 0;
-                        double ox_ = x_lo + old.x, oy_ = y_lo + old.y, nx_ = x_lo + pt.x, ny_ = y_lo + pt.y;
-                        if (ox_ >= g.Lx) ox_ -= g.Lx; if (oy_ >= g.Ly) oy_ -= g.Ly;
-                        if (nx_ >= g.Lx) nx_ -= g.Lx; if (ny_ >= g.Ly) ny_ -= g.Ly;
-                        tr.old_x = ox_; tr.old_y = oy_; tr.new_x = nx_; tr.new_y = ny_;
-                        tr.dE = evaluated ? dE : nan("");
-                        a.trace[slot] = tr;
-                    }
-                }
-                __syncwarp();
-            }
-
-            // ---- write the cell back (absolute coordinates) ----
-            if (dirty) {
-                for (int s = lane; s < n_own; s += 32) {
-                    const double2 u = own[s];
-                    double x = x_lo + u.x, y = y_lo + u.y;
-                    if (x >= g.Lx) x -= g.Lx; else if (x < 0.0) x += g.Lx;
-                    if (y >= g.Ly) y -= g.Ly; else if (y < 0.0) y += g.Ly;
-                    a.pos[(size_t)cell * K + s] = make_double2(x, y);
-                    if (a.ids) a.ids[(size_t)cell * K + s] = own_id[s];
-                }
-                if (lane == 0) a.cnt[cell] = n_own;
-            }
-        }
-    }
-
-    // ---- CTA epilogue: deterministic dU partial, integer counters ----
-    if (lane == 0) {
-        red[wib] = dU_total;
-        cred[wib][0] = c_att[0]; cred[wib][1] = c_att[1]; cred[wib][2] = c_att[2];
-        cred[wib][3] = c_acc[0]; cred[wib][4] = c_acc[1]; cred[wib][5] = c_acc[2];
-        cred[wib][6] = c_ovf;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < wpb; ++i) s += red[i];
-        a.partial_dU[blockIdx.x] = s;
-    }
-    if (threadIdx.x < 7) {
-        unsigned long long s = 0;
-        for (int i = 0; i < wpb; ++i) s += cred[i][threadIdx.x];
-        if (s) atomicAdd(&a.counters[threadIdx.x], s);
-    }
-}
+#include "sweep_kernel.cuh"

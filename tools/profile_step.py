@@ -1,0 +1,15 @@
+#!/usr/bin/env python
+"""Short driver for ncu: config #4 (1M particles, GCMC LJ), a few sweeps + one energy reduction.
+Usage: python tools/profile_step.py [sweeps]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+import montecarlo_simulation_b200 as m
+
+sweeps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+wl = bench.workload(1, 0, 1_000_000)
+with m.Context(wl["L"], wl["L"], bench.RCUT, T=bench.T_BENCH, activity=bench.Z_LJ_T1_RHO05, delta=bench.DELTA, seed=42) as ctx:
+    ctx.upload(wl["xy"])
+    st = ctx.run_sweeps(sweeps, disp_per_particle=1, gc_per_cell=1)
+    U, W, N = ctx.total_energy_virial(resync=True)
+    print("N=%d U=%.6f moves=%d sweep_ms=%.3f energy_ms=%.3f" % (N, U, sum(st["attempted"]), ctx.info().last_sweep_ms, ctx.info().last_energy_ms))
