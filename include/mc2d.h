@@ -160,6 +160,16 @@ int mc2d_calc_neighbor_counts(mc2d_ctx *ctx, const double *xy, long long n, int 
 int mc2d_calc_point_energies(mc2d_ctx *ctx, const double *xy, long long n, const double *points,
                              const int *exclude, long long nq, double *energy_out, int *count_out);
 
+/* the neighbour LIST of particle query_index (>= 0; self skipped by index, CellList::getNeighbors,
+ * cell_list.cpp:43-70) or, with query_index < 0, of the point (qx, qy) (getNeighbors2,
+ * cell_list.cpp:72-101): (j, r^2) pairs in the reference's visiting order.  *count_out = list length
+ * (may exceed cap; only cap entries are written). */
+int mc2d_calc_neighbor_list(mc2d_ctx *ctx, const double *xy, long long n, long long query_index, double qx,
+                            double qy, int *out_j, double *out_r2, int cap, int *count_out);
+/* brute-force U and W over all pairs (computeTotalEnergy / computeTotalVirial,
+ * thermodynamic_calculator.cpp:56-101) — O(N^2), the reference's test truth */
+int mc2d_calc_energy_virial_bruteforce(mc2d_ctx *ctx, const double *xy, long long n, double *U, double *W);
+
 /* -- trial log (parity hook for per-trial dE of the sweep kernel) ----------------------------------- */
 typedef struct {
     int pass;        /* 0..3 position of the colour pass inside the sweep */

@@ -76,7 +76,7 @@ EXPORTS = [
     "mc2d_set_delta", "mc2d_set_activity", "mc2d_total_energy_virial", "mc2d_calc_energy_virial",
     "mc2d_calc_cell_ids", "mc2d_calc_neighbor_counts", "mc2d_calc_point_energies", "mc2d_run_sweep_traced",
     "mc2d_comm_unique_id", "mc2d_comm_init", "mc2d_allreduce_stats", "mc2d_get_info", "mc2d_get_stream",
-    "mc2d_synchronize", "mc2d_set_kernel_timing",
+    "mc2d_synchronize", "mc2d_set_kernel_timing", "mc2d_calc_neighbor_list", "mc2d_calc_energy_virial_bruteforce",
 ]
 
 _lib = None
@@ -125,6 +125,8 @@ def load_library() -> C.CDLL:
     L.mc2d_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.mc2d_synchronize.argtypes = [vp]
     L.mc2d_set_kernel_timing.argtypes = [vp, i]
+    L.mc2d_calc_neighbor_list.argtypes = [vp, vp, ll, ll, d, d, vp, vp, i, ip]
+    L.mc2d_calc_energy_virial_bruteforce.argtypes = [vp, vp, ll, dp, dp]
     _lib = L
     return L
 
@@ -358,6 +360,23 @@ class Context:
                                                     ex.ctypes.data if ex is not None else None, nq, e.ctypes.data,
                                                     c.ctypes.data))
         return (e[:nq], c[:nq]) if with_counts else e[:nq]
+
+    def calc_neighbor_list(self, xy, index=None, point=None, cap=4096):
+        """CellList::getNeighbors(index) or getNeighbors2(point): (j, r2) in the reference's order."""
+        a, n = self._xy(xy)
+        j = np.empty(cap, dtype=np.int32)
+        r2 = np.empty(cap, dtype=np.float64)
+        cnt = C.c_int()
+        qx, qy = (0.0, 0.0) if point is None else (float(point[0]), float(point[1]))
+        self._check(self.L.mc2d_calc_neighbor_list(self.h, a.ctypes.data, n, -1 if index is None else int(index), qx,
+                                                   qy, j.ctypes.data, r2.ctypes.data, cap, C.byref(cnt)))
+        return j[: cnt.value].copy(), r2[: cnt.value].copy()
+
+    def calc_energy_virial_bruteforce(self, xy):
+        a, n = self._xy(xy)
+        U, W = C.c_double(), C.c_double()
+        self._check(self.L.mc2d_calc_energy_virial_bruteforce(self.h, a.ctypes.data, n, C.byref(U), C.byref(W)))
+        return U.value, W.value
 
     # -- multi-GPU ----------------------------------------------------------------------------------
     def comm_init(self, unique_id: bytes):

@@ -787,6 +787,67 @@ extern "C" int mc2d_calc_point_energies(mc2d_ctx *ctx, const double *xy, long lo
     return MC2D_OK;
 }
 
+extern "C" int mc2d_calc_neighbor_list(mc2d_ctx *ctx, const double *xy, long long n, long long query_index,
+                                       double qx, double qy, int *out_j, double *out_r2, int cap, int *count_out) {
+    if (!ctx || (n > 0 && !xy) || cap < 0 || !count_out || (cap > 0 && (!out_j || !out_r2)) || query_index >= n)
+        return MC2D_ERR_INVALID;
+    CsrView v;
+    int rc = build_reference_csr(ctx, xy, n, &v);
+    if (rc) return rc;
+    int qs = -1;
+    if (query_index >= 0) {  // sorted position of the caller's particle: invert the permutation on the host
+        std::vector<int> perm((size_t)n);
+        CU(cudaMemcpyAsync(perm.data(), ctx->sids.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (long long k = 0; k < n; ++k)
+            if (perm[(size_t)k] == (int)query_index) {
+                qs = (int)k;
+                break;
+            }
+    }
+    CU(ctx->outC.ensure(sizeof(int) * (size_t)(cap + 2)));
+    CU(ctx->outE.ensure(sizeof(double) * (size_t)(cap + 1)));
+    int *d_count = ctx->outC.as<int>() + cap;
+    k_neighbor_list<<<1, 32, 0, ctx->stream>>>(v, ctx->r2cut, qs, qx, qy, ctx->outC.as<int>(), ctx->outE.as<double>(),
+                                               cap, d_count);
+    ctx->launches++;
+    int cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    *count_out = cnt;
+    const int m = std::min(cnt, cap);
+    if (m > 0) {
+        CU(cudaMemcpy(out_j, ctx->outC.p, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(out_r2, ctx->outE.p, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost));
+    }
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_calc_energy_virial_bruteforce(mc2d_ctx *ctx, const double *xy, long long n, double *U, double *W) {
+    if (!ctx || (n > 0 && !xy)) return MC2D_ERR_INVALID;
+    int rc = h2d_positions(ctx, xy, n);
+    if (rc) return rc;
+    const int nn = (int)n, nblocks = std::max(1, (nn + 255) / 256);
+    CU(ctx->partial.ensure(sizeof(double) * 2 * (size_t)nblocks));
+    double *pU = ctx->partial.as<double>(), *pW = pU + nblocks;
+    DISPATCH_POT(ctx->prm.potential, {
+        k_bruteforce<POT><<<nblocks, 256, 0, ctx->stream>>>(ctx->xy_in.as<double2>(), nn, ctx->prm.Lx, ctx->prm.Ly,
+                                                            1.0 / ctx->prm.Lx, 1.0 / ctx->prm.Ly, ctx->pp,
+                                                            ctx->r2cut, pU, pW);
+    });
+    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(pU, nblocks, 1.0, ctx->d_energy + 1, 0);
+    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(pW, nblocks, 1.0, ctx->d_energy + 2, 0);
+    ctx->launches += 3;
+    double uw[2];
+    CU(cudaMemcpyAsync(uw, ctx->d_energy + 1, sizeof uw, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    if (U) *U = uw[0];
+    if (W) *W = uw[1];
+    return MC2D_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // the step loop
 // ------------------------------------------------------------------------------------------------

@@ -329,6 +329,87 @@ __global__ void __launch_bounds__(256) k_point_energy(CsrView v, PairParams pp, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// K6' — the neighbour LIST of one particle or point, in the reference's visiting order
+//   CellList::getNeighbors / getNeighbors2 (cell_list.cpp:43-101): ddx outer, ddy inner, bucket
+//   order, (j, r^2) pairs.  One warp, ballot compaction keeps the order.  Parity/test hook.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_neighbor_list(CsrView v, double r2cut, int query_sorted /* >=0: a particle (sorted position) */,
+                                double qx, double qy, int *out_j, double *out_r2, int cap, int *count_out) {
+    const int lane = threadIdx.x & 31;
+    int cx, cy, self = -1;
+    if (query_sorted >= 0) {  // the cell recorded at build time (cell_list.cpp:45)
+        const double2 p = v.pos[query_sorted];
+        qx = p.x;
+        qy = p.y;
+        self = query_sorted;
+    }
+    cx = wrap_index((int)floor(qx / v.cdx), v.nx);
+    cy = wrap_index((int)floor(qy / v.cdy), v.ny);
+    const double hLx = 0.5 * v.Lx, hLy = 0.5 * v.Ly;
+    int nout = 0;
+    for (int ddx = -1; ddx <= 1; ++ddx)
+        for (int ddy = -1; ddy <= 1; ++ddy) {
+            int b, n;
+            v.range(cx, cy, ddx, ddy, b, n);
+            for (int s0 = 0; s0 < n; s0 += 32) {
+                const int j = b + s0 + lane;
+                bool hit = false;
+                double r2 = 0.0;
+                if (s0 + lane < n && j != self) {
+                    const double2 pj = v.pos[j];
+                    r2 = exact_r2(qx, qy, pj.x, pj.y, v.Lx, v.Ly, hLx, hLy);
+                    hit = r2 <= r2cut;
+                }
+                const unsigned m = __ballot_sync(FULL_MASK, hit);
+                if (hit) {
+                    const int off = nout + __popc(m & ((1u << lane) - 1u));
+                    if (off < cap) {
+                        out_j[off] = v.perm[j];
+                        out_r2[off] = r2;
+                    }
+                }
+                nout += __popc(m);
+            }
+        }
+    if (lane == 0) *count_out = nout;
+}
+
+// ---------------------------------------------------------------------------------------------
+// brute-force U and W over all i<j (computeTotalEnergy / computeTotalVirial,
+// thermodynamic_calculator.cpp:56-101; minimum image by dx -= Lx*round(dx*invLx), initial.cpp:43-51).
+// O(N^2): the reference uses it as test truth only; same role here.  One thread per i.
+// ---------------------------------------------------------------------------------------------
+template <int POT>
+__global__ void __launch_bounds__(256) k_bruteforce(const double2 *pos, int n, double Lx, double Ly, double invLx,
+                                                    double invLy, PairParams pp, double r2cut, double *partU,
+                                                    double *partW) {
+    __shared__ double red[32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double u = 0.0, w = 0.0;
+    if (i < n) {
+        const double2 pi = pos[i];
+        for (int j = i + 1; j < n; ++j) {
+            const double2 pj = pos[j];
+            double dx = __dsub_rn(pi.x, pj.x), dy = __dsub_rn(pi.y, pj.y);
+            dx = __dsub_rn(dx, __dmul_rn(Lx, round(__dmul_rn(dx, invLx))));
+            dy = __dsub_rn(dy, __dmul_rn(Ly, round(__dmul_rn(dy, invLy))));
+            const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            if (r2 <= r2cut) {
+                double pu, pw;
+                pair_uw<POT>(r2, pp, pu, pw);
+                u += pu;
+                w += pw;
+            }
+        }
+    }
+    const double su = block_sum(u, red), sw = block_sum(w, red);
+    if (threadIdx.x == 0) {
+        partU[blockIdx.x] = su;
+        partW[blockIdx.x] = sw;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1 — cell keys.  mode 0: reference grid, key = cx + cy*nx with the arithmetic of
 // cell_list.cpp:103-109 (IEEE division, floor, modular wrap): bit-exact cell ids.
 // mode 1: checkerboard grid (shifted origin, column-major stored index); particles outside this
