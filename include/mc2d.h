@@ -83,6 +83,9 @@ typedef struct {
     int disp_per_particle; /* 0 disables displacements */
     int gc_per_cell;       /* 0 = NVT */
     int shift_grid;        /* 1: random grid shift before every sweep (ergodicity); 0: frozen grid */
+    int disp_per_cell;     /* > 0: every non-empty cell gets exactly this many displacement trials per visit
+                            * instead of disp_per_particle * n_cell (a fixed "nselect": same ensemble, all
+                            * cells of a warp finish together) */
 } mc2d_sweep_plan;
 
 typedef struct mc2d_ctx mc2d_ctx;

@@ -45,7 +45,8 @@ class Stats(C.Structure):
 
 
 class SweepPlan(C.Structure):
-    _fields_ = [("disp_per_particle", C.c_int), ("gc_per_cell", C.c_int), ("shift_grid", C.c_int)]
+    _fields_ = [("disp_per_particle", C.c_int), ("gc_per_cell", C.c_int), ("shift_grid", C.c_int),
+                ("disp_per_cell", C.c_int)]
 
 
 class Trial(C.Structure):
@@ -273,14 +274,14 @@ class Context:
         return (xy[: m.value], ids[: m.value]) if with_ids else xy[: m.value]
 
     # -- step loop --------------------------------------------------------------------------------
-    def run_sweeps(self, nsweeps, disp_per_particle=1, gc_per_cell=0, shift_grid=True) -> dict:
-        plan = SweepPlan(disp_per_particle, gc_per_cell, int(shift_grid))
+    def run_sweeps(self, nsweeps, disp_per_particle=1, gc_per_cell=0, shift_grid=True, disp_per_cell=0) -> dict:
+        plan = SweepPlan(disp_per_particle, gc_per_cell, int(shift_grid), disp_per_cell)
         st = Stats()
         self._check(self.L.mc2d_run_sweeps(self.h, nsweeps, C.byref(plan), C.byref(st)))
         return st.as_dict()
 
-    def run_sweep_traced(self, disp_per_particle=1, gc_per_cell=0, shift_grid=True, cap=1 << 20):
-        plan = SweepPlan(disp_per_particle, gc_per_cell, int(shift_grid))
+    def run_sweep_traced(self, disp_per_particle=1, gc_per_cell=0, shift_grid=True, cap=1 << 20, disp_per_cell=0):
+        plan = SweepPlan(disp_per_particle, gc_per_cell, int(shift_grid), disp_per_cell)
         st = Stats()
         buf = np.zeros(cap, dtype=TRIAL_DTYPE)
         n = C.c_longlong()

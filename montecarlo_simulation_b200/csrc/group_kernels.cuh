@@ -1,0 +1,157 @@
+// group_kernels.cuh — production variants of K4 (energy + virial) and K1' (re-bin) with G lanes per
+// cell and 32/G cells per warp (same reasoning as sweep_kernel_g.cuh: a 2.5-sigma LJ cell at
+// rho = 0.5 has ~16 half-shell / ~28 full-shell candidates, which does not fill a warp; the per-cell
+// fixed cost — nine count loads, prefix, candidate decode — is shared by 32/G cells).
+// The warp-per-cell versions in mc2d_kernels.cuh remain for the per-particle parity hooks (PERP).
+#pragma once
+
+template <int POT>
+__device__ __forceinline__ void pair_uw_fast(double r2, const PairParams &pp, double &u, double &w) {
+    if (POT == POT_LJ) {
+        const double r2inv = fast_rcp(r2), r6inv = r2inv * r2inv * r2inv;
+        u = 4.0 * r6inv * (r6inv - 1.0);
+        w = 48.0 * r6inv * (r6inv - 0.5);
+    } else if (POT == POT_WCA) {
+        const double r2inv = fast_rcp(r2), r6inv = r2inv * r2inv * r2inv;
+        const bool in = r2 < 1.2599;
+        u = in ? 4.0 * r6inv * (r6inv - 1.0) + 1.0 : 0.0;
+        w = in ? 48.0 * r6inv * (r6inv - 0.5) : 0.0;
+    } else {
+        pair_uw<POT>(r2, pp, u, w);
+    }
+}
+
+// K4, G lanes per cell.  half = 1: own cell (j > i) + the 4 forward neighbours; half = 0: the
+// reference's directed 3x3 double count (caller halves).  Distances use the exact reference
+// arithmetic (exact_r2); LJ/WCA take the Newton reciprocal (<= 1 ulp from the IEEE quotient).
+template <class V, int POT, int G>
+__global__ void __launch_bounds__(256) k_energy_virial_g(V v, PairParams pp, double r2cut, int half, double *partU,
+                                                         double *partW, unsigned long long *pair_stats) {
+    __shared__ double red[32];
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int gi = lane / G, sl = lane % G;
+    const int w = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + gi;
+    const double Lx = v_Lx(v), Ly = v_Ly(v), hLx = 0.5 * Lx, hLy = 0.5 * Ly;
+    double accU = 0.0, accW = 0.0;
+    unsigned int tests = 0, evals = 0;
+    int cx = 0, cy = 0, b0 = 0, n0 = 0;
+    const bool has = w < v.ncells();
+    if (has) {
+        v.cell(w, cx, cy);
+        v.range(cx, cy, 0, 0, b0, n0);
+    }
+    int tb[9], ts[10];
+    ts[0] = 0;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        const int ddx = c / 3 - 1, ddy = c % 3 - 1;  // ddx outer, ddy inner (cell_list.cpp:49-50)
+        int b = 0, n = 0;
+        bool use = has && n0 > 0 && v.range(cx, cy, ddx, ddy, b, n);
+        if (half) use = use && ((ddx == 0 && ddy == 0) || ddx == 1 || (ddx == 0 && ddy == 1));
+        tb[c] = b;
+        ts[c + 1] = ts[c] + (use ? n : 0);
+    }
+    const int M = ts[9];
+    const int KM = warp_max_int(M), N0 = warp_max_int(n0);
+    for (int k = sl; k < KM; k += G) {
+        const bool vk = k < M;
+        int cb = tb[0], cs = 0;
+#pragma unroll
+        for (int q = 1; q < 9; ++q)
+            if (k >= ts[q]) { cb = tb[q]; cs = ts[q]; }
+        const int j = cb + (k - cs);
+        const bool same_cell = (cb == b0);
+        const int jrel = j - b0;
+        double2 pj = make_double2(0.0, 0.0);
+        if (vk) pj = v.pos[j];
+        for (int i = 0; i < N0; ++i) {
+            const bool ok = vk && i < n0 && !(same_cell && (half ? (jrel <= i) : (jrel == i)));
+            double2 pi = make_double2(1.0, 1.0);
+            if (ok) pi = v.pos[b0 + i];
+            const double r2 = exact_r2(pi.x, pi.y, pj.x, pj.y, Lx, Ly, hLx, hLy);
+            const bool hit = ok && r2 <= r2cut;  // inclusive, cell_list.cpp:62
+            double u, wv;
+            pair_uw_fast<POT>(hit ? r2 : 1.0, pp, u, wv);
+            accU += hit ? u : 0.0;
+            accW += hit ? wv : 0.0;
+            tests += ok;
+            evals += hit;
+        }
+    }
+    const double sU = block_sum(accU, red);
+    const double sW = block_sum(accW, red);
+    if (threadIdx.x == 0) {
+        partU[blockIdx.x] = sU;
+        partW[blockIdx.x] = sW;
+    }
+    const unsigned int t = (unsigned int)warp_sum_int((int)tests), e = (unsigned int)warp_sum_int((int)evals);
+    if (lane == 0 && pair_stats && (t | e)) {
+        atomicAdd(&pair_stats[0], (unsigned long long)t);
+        atomicAdd(&pair_stats[1], (unsigned long long)e);
+    }
+}
+
+// K1', G lanes per new cell: gather from the 3x3 old cells by ballot compaction inside the group.
+// Same result (cell contents AND slot order) as k_rebin.
+template <int G>
+__global__ void __launch_bounds__(256) k_rebin_g(const double2 *pos_o, const int *cnt_o, const int *ids_o,
+                                                 double2 *pos_n, int *cnt_n, int *ids_n, Grid gn, int *err) {
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int gi = lane / G, sl = lane % G;
+    const int w = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + gi;
+    const bool has = w < gn.ncol * gn.ny;
+    const int lcx = gn.ghost + (has ? w / gn.ny : 0), cy = has ? w % gn.ny : 0;
+    const int gcx = gn.col0 + (lcx - gn.ghost);
+    const int K = gn.K;
+    const size_t obase = (size_t)(lcx * gn.ny + cy) * K;
+    int tc[9], ts[10];
+    ts[0] = 0;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        const int ddx = c / 3 - 1, ddy = c % 3 - 1;
+        const bool dup = (gn.nx == 2 && ddx < 0) || (gn.ny == 2 && ddy < 0);
+        int ocx = lcx + ddx, ocy = cy + ddy;
+        if (!gn.ghost) {
+            if (ocx < 0) ocx += gn.nx; else if (ocx >= gn.nx) ocx -= gn.nx;
+        }
+        if (ocy < 0) ocy += gn.ny; else if (ocy >= gn.ny) ocy -= gn.ny;
+        tc[c] = ocx * gn.ny + ocy;
+        ts[c + 1] = ts[c] + ((has && !dup) ? cnt_o[tc[c]] : 0);
+    }
+    const int M = ts[9];
+    const int KM = warp_max_int(M);
+    const unsigned gmask = ((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << (gi * G);
+    int nout = 0;
+    for (int k0 = 0; k0 < KM; k0 += G) {
+        const int k = k0 + sl;
+        bool take = false;
+        double2 p = make_double2(0.0, 0.0);
+        size_t src = 0;
+        if (k < M) {
+            int cc = tc[0], cs = 0;
+#pragma unroll
+            for (int q = 1; q < 9; ++q)
+                if (k >= ts[q]) { cc = tc[q]; cs = ts[q]; }
+            src = (size_t)cc * K + (k - cs);
+            p = pos_o[src];
+            int ngx, ncy;
+            sweep_cell_of(gn, p.x, p.y, ngx, ncy);
+            take = (ngx == gcx && ncy == cy);
+        }
+        const unsigned m = __ballot_sync(FULL_MASK, take) & gmask;
+        if (take) {
+            const int off = nout + __popc(m & ((1u << lane) - 1u));
+            if (off < K) {
+                pos_n[obase + off] = p;
+                if (ids_n) ids_n[obase + off] = ids_o[src];
+            }
+        }
+        nout += __popc(m);
+    }
+    if (has && sl == 0) {
+        cnt_n[lcx * gn.ny + cy] = min(nout, K);
+        if (nout > K) atomicMax(&err[0], nout);
+    }
+}

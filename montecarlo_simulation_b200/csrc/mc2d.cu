@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -126,6 +127,8 @@ struct mc2d_ctx {
     double last_sweep_ms = 0, last_energy_ms = 0;
     long long last_tests = 0, last_evals = 0;
     unsigned long long attr_set = 0;  // bitmask of k_sweep instantiations whose smem attribute is set
+    unsigned long long attr_set_g = 0;  // same for k_sweep_g
+    long long n_last = 0;             // last known particle count (sizes the neighbour staging area)
     bool ktiming = false;
     std::vector<cudaEvent_t> kev;  // event pool for per-kernel timing
     std::vector<int> kev_kind;     // 0 sweep, 1 rebin (one entry per event PAIR used in this call)
@@ -531,6 +534,7 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
                                                              ctx->d_err);
     ctx->launches++;
     ctx->have_particles = true;
+    ctx->n_last = kept;
     ctx->sweep = 0;
     CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     if (g.ghost && ctx->have_comm) {
@@ -558,6 +562,7 @@ static int count_particles(mc2d_ctx *ctx, long long *n) {
     CU(cudaMemcpyAsync(&v, ctx->d_pair_stats + 2, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     *n = (long long)v;
+    ctx->n_last = *n;
     return MC2D_OK;
 }
 
@@ -608,7 +613,10 @@ extern "C" int mc2d_download(mc2d_ctx *ctx, double *xy, int *ids, long long cap,
 template <class V>
 static int launch_energy(mc2d_ctx *ctx, const V &view, int ncells, int half, bool perp, int *count_out,
                          double *eloc_out, double *U, double *W) {
-    const int wpb = 8, nblocks = std::max(1, (ncells + wpb - 1) / wpb);
+    // per-particle outputs: one warp per cell; totals only: 8 lanes per cell, 4 cells per warp
+    constexpr int GE = 8;
+    const int wpb = 8, cells_per_block = perp ? wpb : wpb * (32 / GE);
+    const int nblocks = std::max(1, (ncells + cells_per_block - 1) / cells_per_block);
     CU(ctx->partial.ensure(sizeof(double) * 2 * (size_t)nblocks));
     double *pU = ctx->partial.as<double>(), *pW = pU + nblocks;
     CU(cudaMemsetAsync(ctx->d_pair_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
@@ -618,8 +626,8 @@ static int launch_energy(mc2d_ctx *ctx, const V &view, int ncells, int half, boo
             k_energy_virial<V, POT, true><<<nblocks, wpb * 32, 0, ctx->stream>>>(
                 view, ctx->pp, ctx->r2cut, half, pU, pW, ctx->d_pair_stats, count_out, eloc_out);
         else
-            k_energy_virial<V, POT, false><<<nblocks, wpb * 32, 0, ctx->stream>>>(
-                view, ctx->pp, ctx->r2cut, half, pU, pW, ctx->d_pair_stats, nullptr, nullptr);
+            k_energy_virial_g<V, POT, GE><<<nblocks, wpb * 32, 0, ctx->stream>>>(view, ctx->pp, ctx->r2cut, half, pU,
+                                                                                   pW, ctx->d_pair_stats);
     });
     const double scale = half ? 1.0 : 0.5;  // directed double count is halved (thermodynamic_calculator.cpp:211,232)
     k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(pU, nblocks, scale, ctx->d_energy + 1, 0);
@@ -862,6 +870,17 @@ static int launch_sweep_kernel(mc2d_ctx *ctx, const SweepArgs &a, int nblocks, i
     return MC2D_OK;
 }
 
+template <int POT, int G, bool TRACE>
+static int launch_sweep_g(mc2d_ctx *ctx, const SweepArgs &a, int nblocks, int wpb, size_t smem, int nb_cap, int inst) {
+    if (!(ctx->attr_set_g & (1ull << inst))) {
+        CU(cudaFuncSetAttribute(k_sweep_g<POT, G, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ctx->attr_set_g |= (1ull << inst);
+    }
+    k_sweep_g<POT, G, TRACE><<<nblocks, wpb * 32, smem, ctx->stream>>>(a, nb_cap);
+    ctx->launches++;
+    return MC2D_OK;
+}
+
 static int ktime_begin(mc2d_ctx *ctx, int kind) {
     if (!ctx->ktiming) return MC2D_OK;
     const size_t need = 2 * (ctx->kev_kind.size() + 1);
@@ -883,9 +902,9 @@ static int ktime_end(mc2d_ctx *ctx) {
 static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_plan *plan, mc2d_trial *trace,
                            long long trace_cap, long long *trace_n) {
     if (!ctx->have_particles) FAIL(MC2D_ERR_STATE, "no particles uploaded");
-    if (!plan || plan->disp_per_particle < 0 || plan->gc_per_cell < 0 || nsweeps < 0)
+    if (!plan || plan->disp_per_particle < 0 || plan->gc_per_cell < 0 || plan->disp_per_cell < 0 || nsweeps < 0)
         FAIL(MC2D_ERR_INVALID, "bad sweep plan");
-    if (plan->disp_per_particle * 1024LL + plan->gc_per_cell >= (1 << 28))
+    if (plan->disp_per_particle * 1024LL + plan->disp_per_cell + plan->gc_per_cell >= (1 << 28))
         FAIL(MC2D_ERR_INVALID, "too many trials per cell visit");
     CU(cudaSetDevice(ctx->dev));
     Grid &g = ctx->g;
@@ -897,7 +916,24 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
     if (per_warp * wpb > 200 * 1024) FAIL(MC2D_ERR_CELL_OVERFLOW, "cell capacity %d needs too much shared memory", K);
     const int nact = (g.ncol / 2) * (g.ny / 2);
-    const int nblocks = std::max(1, (nact + wpb - 1) / wpb);
+    // Kernel choice: G lanes per cell (k_sweep_g) unless the grid needs the per-pair minimum image.
+    // G follows the expected number of candidates per cell (9 cells x mean occupancy): 8 lanes for
+    // LJ-like neighbourhoods (~28 candidates), 4 for short-range ones (~6).  MC2D_SWEEP_G overrides
+    // (0 = one warp per cell), for tuning.
+    int G = 0, nb_cap = 0;
+    size_t per_group = 0;
+    if (!minimg) {
+        const double n_c = (double)std::max<long long>(ctx->n_last, 1) / std::max(1, g.ncol * g.ny);
+        G = (ideal || 9.0 * n_c < 14.0) ? 4 : 8;
+        if (const char *e = getenv("MC2D_SWEEP_G")) G = atoi(e);
+        if (G != 0 && G != 4 && G != 8 && G != 16) FAIL(MC2D_ERR_INVALID, "MC2D_SWEEP_G must be 0, 4, 8 or 16");
+        nb_cap = ideal ? 0 : std::min(8 * K, even_up((int)(8.0 * n_c * 1.6 + 12.0), 4));
+        per_group = (size_t)(nb_cap + K) * sizeof(double2) + (ctx->use_ids ? (size_t)K * sizeof(int) : 0);
+        if (G && per_group * (32 / G) * 8 > 200 * 1024) G = 0;  // very large cells: one warp per cell
+    }
+    if (G) wpb = 8;
+    const int cells_per_block = G ? wpb * (32 / G) : wpb;
+    const int nblocks = std::max(1, (nact + cells_per_block - 1) / cells_per_block);
     CU(ctx->partial.ensure(sizeof(double) * 4 * (size_t)nblocks));
     // per-CTA dU accumulators live across the whole batch and are reduced once at its end
     CU(cudaMemsetAsync(ctx->partial.p, 0, sizeof(double) * 4 * (size_t)nblocks, ctx->stream));
@@ -919,11 +955,14 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             gn.oy = sy;
             const int nb = 1 - ctx->cur;
             if (int rc = ktime_begin(ctx, 1)) return rc;
-            k_rebin<<<(ncell_owned + 7) / 8, 256, 0, ctx->stream>>>(ctx->pos[ctx->cur], ctx->cnt[ctx->cur],
-                                                                    ctx->use_ids ? ctx->ids[ctx->cur] : nullptr,
-                                                                    ctx->pos[nb], ctx->cnt[nb],
-                                                                    ctx->use_ids ? ctx->ids[nb] : nullptr, g, gn,
-                                                                    ctx->d_err);
+            if (K <= 64)  // 8 lanes per new cell, 4 cells per warp
+                k_rebin_g<8><<<(ncell_owned + 31) / 32, 256, 0, ctx->stream>>>(
+                    ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->use_ids ? ctx->ids[ctx->cur] : nullptr, ctx->pos[nb],
+                    ctx->cnt[nb], ctx->use_ids ? ctx->ids[nb] : nullptr, gn, ctx->d_err);
+            else  // very populated cells: one warp per new cell
+                k_rebin<<<(ncell_owned + 7) / 8, 256, 0, ctx->stream>>>(
+                    ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->use_ids ? ctx->ids[ctx->cur] : nullptr, ctx->pos[nb],
+                    ctx->cnt[nb], ctx->use_ids ? ctx->ids[nb] : nullptr, g, gn, ctx->d_err);
             if (int rc = ktime_end(ctx)) return rc;
             ctx->launches++;
             ctx->cur = nb;
@@ -949,6 +988,7 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             a.seed_lo = (uint32_t)ctx->prm.seed;
             a.seed_hi = (uint32_t)(ctx->prm.seed >> 32);
             a.disp_mult = plan->disp_per_particle;
+            a.disp_cell = plan->disp_per_cell;
             a.n_gc = plan->gc_per_cell;
             a.p_ins = ctx->p_ins;
             a.p_del = ctx->p_del;
@@ -957,13 +997,23 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             a.trace = trace ? ctx->trace_buf.as<mc2d_trial>() : nullptr;
             a.trace_n = ctx->d_trace_n;
             a.trace_cap = trace_cap;
-            const size_t smem = per_warp * wpb;
+            const size_t smem = G ? per_group * (32 / G) * wpb : per_warp * wpb;
             int rc = ktime_begin(ctx, 0);
             if (rc) return rc;
             const int pot = ctx->prm.potential;
             DISPATCH_POT(pot, {
                 const int inst = POT * 4 + (minimg ? 2 : 0) + (trace ? 1 : 0);
-                if (trace) {
+                const int inst_g = POT * 8 + (G == 4 ? 0 : G == 8 ? 2 : 4) + (trace ? 1 : 0);
+                if (G == 4) {
+                    if (trace) rc = launch_sweep_g<POT, 4, true>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
+                    else rc = launch_sweep_g<POT, 4, false>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
+                } else if (G == 8) {
+                    if (trace) rc = launch_sweep_g<POT, 8, true>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
+                    else rc = launch_sweep_g<POT, 8, false>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
+                } else if (G == 16) {
+                    if (trace) rc = launch_sweep_g<POT, 16, true>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
+                    else rc = launch_sweep_g<POT, 16, false>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
+                } else if (trace) {
                     if (minimg) rc = launch_sweep_kernel<POT, true, true>(ctx, a, nblocks, wpb, smem, inst);
                     else rc = launch_sweep_kernel<POT, false, true>(ctx, a, nblocks, wpb, smem, inst);
                 } else {

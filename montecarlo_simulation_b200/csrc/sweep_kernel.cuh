@@ -29,7 +29,7 @@ struct SweepArgs {
     double r2cut, beta, zA, delta;
     int colour, pass;
     uint32_t sweep_lo, sweep_hi, seed_lo, seed_hi;
-    int disp_mult, n_gc;
+    int disp_mult, disp_cell, n_gc;
     double p_ins, p_del;
     double *partial_dU;            // one accumulator per CTA, private to it, summed at the end of the batch
     unsigned long long *counters;  // [0..2] attempted, [3..5] accepted, [6] overflow
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256, MC2D_SWEEP_MIN_BLOCKS) k_sweep(SweepArgs 
         const double x_lo = g.ox + gcx * g.dx, y_lo = g.oy + cy * g.dy;
         const double hLx = 0.5 * g.Lx, hLy = 0.5 * g.Ly;
         int n_own = a.cnt[cell];
-        const int n_disp = a.disp_mult * n_own;
+        const int n_disp = n_own > 0 ? (a.disp_cell > 0 ? a.disp_cell : a.disp_mult * n_own) : 0;
         if (n_disp > 0 || a.n_gc > 0) {
             // ---- stage the 8 neighbour cells, flattened, into cand[0..M) ----
             int M = 0;

@@ -455,3 +455,46 @@ def test_one_million_particles_properties(mc, oracle):
         assert N2 == st["n_particles"] and relerr(st["energy"], U2) < 1e-9
     calc = oracle.calc(1.0, 0.0, ol.LJ, 2.5)
     assert relerr(U0, oracle.total_energy_celllist(calc, L, L, xy)) < REL
+
+
+# ---- kernel variants ---------------------------------------------------------------------------------------------------
+
+def test_sweep_kernel_variants_are_bit_identical(mc, monkeypatch):
+    """k_sweep (one warp per cell) and k_sweep_g (G = 4, 8, 16 lanes per cell) run the same algorithm on the
+    same Philox streams: identical configurations, counters and (to rounding of the summation order) energy."""
+    Lx, Ly = 61.0, 47.5
+    xy = lattice(40, 32, Lx, Ly, 0.2, 3)
+    res = {}
+    for G in ("0", "4", "8", "16"):
+        monkeypatch.setenv("MC2D_SWEEP_G", G)
+        with mc.Context(Lx, Ly, 2.5, T=0.9, activity=0.3, delta=0.12, seed=21) as ctx:
+            ctx.upload(xy, np.arange(len(xy), dtype=np.int32))
+            st = ctx.run_sweeps(12, gc_per_cell=2)
+            res[G] = (ctx.download(with_ids=True), st)
+    (p0, i0), s0 = res["0"]
+    for G in ("4", "8", "16"):
+        (p, i), s = res[G]
+        assert p.shape == p0.shape and (p == p0).all() and (i == i0).all(), G
+        assert s["attempted"] == s0["attempted"] and s["accepted"] == s0["accepted"], G
+        assert relerr(s["energy"], s0["energy"]) < 1e-12, G
+
+
+def test_fixed_trials_per_cell_mode(mc, oracle):
+    """disp_per_cell (a fixed number of displacement trials per non-empty cell, HPMC's nselect) keeps the
+    bookkeeping exact and samples the same ensemble: ideal-gas <N> = zV, LJ energy consistent."""
+    Lx = Ly = 45.254834
+    xy = lattice(32, 32, Lx, Ly, 0.2, 42)
+    with mc.Context(Lx, Ly, 2.5, T=1.0, delta=0.1, seed=42) as ctx:
+        ctx.upload(xy)
+        st = ctx.run_sweeps(30, disp_per_cell=3)
+        assert st["n_particles"] == 1024 and st["attempted"][0] > 0 and st["attempted"][0] % 3 == 0
+        U = ctx.total_energy_virial()[0]
+        assert relerr(st["energy"], U) < 1e-9
+        assert relerr(U, oracle.total_energy_celllist(oracle.calc(1.0, 0.0, ol.LJ, 2.5), Lx, Ly, ctx.download())) < REL
+    z, V = 2.0, 40.0 * 40.0
+    with mc.Context(40.0, 40.0, 2.5, potential="Ideal", T=1.0, activity=z, delta=0.3, seed=5) as ctx:
+        ctx.upload(np.random.default_rng(1).uniform(0, 40.0, (int(z * V), 2)))
+        ctx.run_sweeps(200, gc_per_cell=2, disp_per_cell=2)
+        ns = np.array([ctx.run_sweeps(3, gc_per_cell=2, disp_per_cell=2)["n_particles"] for _ in range(1500)])
+    assert abs(ns.mean() - z * V) < 4 * block_se(ns) + 0.01 * math.sqrt(z * V)
+    assert abs(ns.var() / (z * V) - 1.0) < 0.2

@@ -7,9 +7,10 @@ import bench
 import montecarlo_simulation_b200 as m
 
 sweeps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+dpc = int(os.environ.get("MC2D_DISP_PER_CELL", "0"))
 wl = bench.workload(1, 0, 1_000_000)
 with m.Context(wl["L"], wl["L"], bench.RCUT, T=bench.T_BENCH, activity=bench.Z_LJ_T1_RHO05, delta=bench.DELTA, seed=42) as ctx:
     ctx.upload(wl["xy"])
-    st = ctx.run_sweeps(sweeps, disp_per_particle=1, gc_per_cell=1)
+    st = ctx.run_sweeps(sweeps, disp_per_particle=1, gc_per_cell=1, disp_per_cell=dpc)
     U, W, N = ctx.total_energy_virial(resync=True)
     print("N=%d U=%.6f moves=%d sweep_ms=%.3f energy_ms=%.3f" % (N, U, sum(st["attempted"]), ctx.info().last_sweep_ms, ctx.info().last_energy_ms))
