@@ -264,6 +264,13 @@ class Context:
         self._check(self.L.mc2d_num_particles(self.h, C.byref(n)))
         return n.value
 
+    def download_into(self, xy: np.ndarray) -> int:
+        """downloads into a caller-owned (e.g. pinned) float64 array of shape (cap, 2); returns the count"""
+        assert xy.dtype == np.float64 and xy.flags["C_CONTIGUOUS"] and xy.ndim == 2 and xy.shape[1] == 2
+        m = C.c_longlong()
+        self._check(self.L.mc2d_download(self.h, xy.ctypes.data, None, xy.shape[0], C.byref(m)))
+        return m.value
+
     def download(self, with_ids=False):
         n = self.num_particles()
         xy = np.empty((max(n, 1), 2), dtype=np.float64)

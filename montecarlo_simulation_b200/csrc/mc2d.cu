@@ -535,8 +535,9 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
     ctx->launches++;
     ctx->have_particles = true;
     ctx->n_last = kept;
-    ctx->sweep = 0;
-    CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    // The sweep counter (part of every Philox counter) is NOT reset: a context that is re-uploaded
+    // between batches (the end-to-end pattern: upload, sweep, download) must not replay the random
+    // streams of its previous batch.  Move counters are left alone too (mc2d_reset_counters).
     if (g.ghost && ctx->have_comm) {
         rc = halo_exchange(ctx, ctx->cur, true, true);
         if (rc) return rc;
@@ -924,14 +925,24 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     size_t per_group = 0;
     if (!minimg) {
         const double n_c = (double)std::max<long long>(ctx->n_last, 1) / std::max(1, g.ncol * g.ny);
-        G = (ideal || 9.0 * n_c < 14.0) ? 4 : 8;
+        // measured on config #4 (28 candidates per cell), 20 sweeps: G=4 7.8 ms, G=8 9.1 ms, G=16 14.8 ms,
+        // one warp per cell 13.6 ms; denser neighbourhoods (> 64 candidates) fill 8 lanes better
+        G = (9.0 * n_c > 64.0) ? 8 : 4;
         if (const char *e = getenv("MC2D_SWEEP_G")) G = atoi(e);
-        if (G != 0 && G != 4 && G != 8 && G != 16) FAIL(MC2D_ERR_INVALID, "MC2D_SWEEP_G must be 0, 4, 8 or 16");
+        if (G != 0 && G != 2 && G != 4 && G != 8 && G != 16)
+            FAIL(MC2D_ERR_INVALID, "MC2D_SWEEP_G must be 0, 2, 4, 8 or 16");
         nb_cap = ideal ? 0 : std::min(8 * K, even_up((int)(8.0 * n_c * 1.6 + 12.0), 4));
         per_group = (size_t)(nb_cap + K) * sizeof(double2) + (ctx->use_ids ? (size_t)K * sizeof(int) : 0);
-        if (G && per_group * (32 / G) * 8 > 200 * 1024) G = 0;  // very large cells: one warp per cell
+        if (G) {
+            wpb = 8;
+            while (wpb > 2 && per_group * (32 / G) * wpb > 72 * 1024) wpb >>= 1;  // keep >= 3 CTAs per SM
+            if (per_group * (32 / G) * wpb > 200 * 1024) G = 0;  // very large cells: one warp per cell
+        }
     }
-    if (G) wpb = 8;
+    if (!G) {
+        wpb = 8;
+        while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+    }
     const int cells_per_block = G ? wpb * (32 / G) : wpb;
     const int nblocks = std::max(1, (nact + cells_per_block - 1) / cells_per_block);
     CU(ctx->partial.ensure(sizeof(double) * 4 * (size_t)nblocks));
@@ -1003,8 +1014,11 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             const int pot = ctx->prm.potential;
             DISPATCH_POT(pot, {
                 const int inst = POT * 4 + (minimg ? 2 : 0) + (trace ? 1 : 0);
-                const int inst_g = POT * 8 + (G == 4 ? 0 : G == 8 ? 2 : 4) + (trace ? 1 : 0);
-                if (G == 4) {
+                const int inst_g = POT * 8 + (G == 2 ? 0 : G == 4 ? 2 : G == 8 ? 4 : 6) + (trace ? 1 : 0);
+                if (G == 2) {
+                    if (trace) rc = launch_sweep_g<POT, 2, true>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
+                    else rc = launch_sweep_g<POT, 2, false>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
+                } else if (G == 4) {
                     if (trace) rc = launch_sweep_g<POT, 4, true>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
                     else rc = launch_sweep_g<POT, 4, false>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
                 } else if (G == 8) {

@@ -42,13 +42,17 @@ struct SweepArgs {
 // plus two Newton steps.  x = 0 gives NaN, which fails every acceptance test (a trial position
 // exactly on top of another particle is rejected).  Only the sweep kernel uses it; the parity
 // hooks (K4/K6) keep the IEEE division of the reference.
+#ifndef MC2D_RCP_NEWTON_STEPS
+#define MC2D_RCP_NEWTON_STEPS 2
+#endif
 __device__ __forceinline__ double fast_rcp(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
+#pragma unroll
+    for (int it = 0; it < MC2D_RCP_NEWTON_STEPS; ++it) {
+        const double e = fma(-x, r, 1.0);
+        r = fma(r, e, r);
+    }
     return r;
 }
 

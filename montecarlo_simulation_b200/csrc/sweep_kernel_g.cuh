@@ -5,26 +5,26 @@
 // convergence) replicated over 32 lanes, while the ~28 candidates of a 2.5-sigma LJ cell at
 // rho = 0.5 fill the lanes once.  Here a warp advances 32/G cells in lock step: the fixed cost is
 // shared by 32/G trials, the candidate loop runs ceil(28/G) iterations with the same lane
-// efficiency, the reduction needs log2(G) steps.  The warp never diverges: a group that has run
-// out of trials (or whose trial left the cell) keeps executing with its lanes predicated off, so
-// all shuffles use the full mask and no BSSY/BSYNC pairs are issued in the trial loop; the cutoff
-// test is a select, not a branch (LJ/WCA).
+// efficiency, the reduction needs log2(G) steps.  The warp never diverges in the trial loop: a
+// group that has run out of trials (or whose trial left the cell) keeps executing with its lanes
+// masked, so all shuffles use the full mask; the cutoff test is a select on r^2, not a branch.
 //
 // Same algorithm, same Philox streams (global cell id, trial index) and the same arithmetic as
 // k_sweep (sweep_kernel.cuh): a run gives bit-identical configurations with either kernel.
-// Per group, shared memory holds nbr[nb_cap] (the 8 neighbour cells, cell-local coordinates)
-// and own[K]; a cell with more than nb_cap neighbours reads them from global memory instead
-// (slow path, rare).  Grids narrower than 4 cells take k_sweep<MINIMG>.
+// Per group, shared memory holds cand[0..Ms) = the 8 neighbour cells in cell-local coordinates,
+// followed by cand[Ms..Ms+n_own) = the cell's own particles.  A cell with more than nb_cap
+// neighbours keeps only its own particles in shared memory (Ms = 0) and reads the neighbours from
+// global memory in a second, cold loop.  Grids narrower than 4 cells take k_sweep<MINIMG>.
 #pragma once
 
-// 3 CTAs/SM: 80 registers, no spills (at 64 registers the kernel spills 80 B and re-reads the
-// thread id inside the candidate loop); shared memory allows 3 CTAs at G = 4 anyway.
+// 3 CTAs/SM: 80 registers, no spills (at 64 registers the kernel spills and re-reads the thread id
+// inside the candidate loop); shared memory allows 3 CTAs at G = 4 anyway.
 // Measured on config #4, 20 sweeps: 7.8 ms (3 CTAs) vs 8.4 ms (4 CTAs).
 #ifndef MC2D_SWEEPG_MIN_BLOCKS
 #define MC2D_SWEEPG_MIN_BLOCKS 3
 #endif
 
-// neighbour q (0..7, skipping the centre) of stored cell (lcx, cy): stored cell index, or -1
+// neighbour q (0..7, skipping the centre) of stored cell (lcx, cy): stored cell index
 __device__ __forceinline__ int nbr_cell_index(const Grid &g, int lcx, int cy, int q) {
     const int o = q + (q >= 4);
     const int ddx = o / 3 - 1, ddy = o % 3 - 1;
@@ -71,22 +71,24 @@ __device__ __noinline__ double2 slow_candidate(const double2 *pos, const int *cn
     return make_double2(1e300, 1e300);
 }
 
-// pair energy with the cutoff as a select (no branch); `valid` masks the lane off
+// Pair energy, cutoff and lane mask without a branch.  For LJ the mask is applied to r^2: a masked
+// or out-of-range pair gets r^2 = 1e300, for which 4 r^-6 (r^-6 - 1) underflows to -0.0 — no select
+// on the result.  The other potentials select the result.
 template <int POT>
 __device__ __forceinline__ double pair_e_sel(double dx, double dy, double r2cut, const PairParams &pp, bool valid) {
     const double r2 = fma(dx, dx, dy * dy);
+    const bool in = valid && r2 <= r2cut;  // inclusive cutoff, cell_list.cpp:62
     if (POT == POT_LJ) {
-        const double r2inv = fast_rcp(r2);
+        const double r2inv = fast_rcp(in ? r2 : 1e300);
         const double r6inv = r2inv * r2inv * r2inv;
-        const double e = 4.0 * r6inv * (r6inv - 1.0);
-        return (valid && r2 <= r2cut) ? e : 0.0;
+        return 4.0 * r6inv * (r6inv - 1.0);
     } else if (POT == POT_WCA) {
         const double r2inv = fast_rcp(r2);
         const double r6inv = r2inv * r2inv * r2inv;
         const double e = 4.0 * r6inv * (r6inv - 1.0) + 1.0;
-        return (valid && r2 <= r2cut && r2 < 1.2599) ? e : 0.0;
+        return (in && r2 < 1.2599) ? e : 0.0;
     } else {
-        return (valid && r2 <= r2cut) ? pair_u<POT>(r2, pp) : 0.0;
+        return in ? pair_u<POT>(r2, pp) : 0.0;
     }
 }
 
@@ -114,9 +116,8 @@ __global__ void __launch_bounds__(256, MC2D_SWEEPG_MIN_BLOCKS) k_sweep_g(SweepAr
     const int gi = lane / G, sl = lane % G;
     const int gid = (blockIdx.x * wpb + wib) * GPW + gi;  // index of this group's active cell
     const size_t per_group = (size_t)(nb_cap + K) * sizeof(double2) + (a.ids ? (size_t)K * sizeof(int) : 0);
-    double2 *nbr = reinterpret_cast<double2 *>(smem_raw + (size_t)(wib * GPW + gi) * per_group);
-    double2 *own = nbr + nb_cap;
-    int *own_id = reinterpret_cast<int *>(own + K);
+    double2 *cand = reinterpret_cast<double2 *>(smem_raw + (size_t)(wib * GPW + gi) * per_group);
+    int *own_id = reinterpret_cast<int *>(cand + nb_cap + K);
 
     const int nay = g.ny >> 1;
     const int nact = (g.ncol >> 1) * nay;
@@ -134,9 +135,8 @@ __global__ void __launch_bounds__(256, MC2D_SWEEPG_MIN_BLOCKS) k_sweep_g(SweepAr
     const int n_gc = has_cell ? a.n_gc : 0;
     const bool work = (n_disp > 0 || n_gc > 0);
 
-    // ---- stage: 8 neighbour cells -> nbr[0..M), own cell -> own[0..n_own) (cell-local coordinates) ----
-    int M = 0;
-    bool staged = true;
+    // ---- stage: 8 neighbour cells -> cand[0..Ms), own cell -> cand[Ms..Ms+n_own) (cell-local) ----
+    int M = 0, Ms = 0;
     if (POT != POT_IDEAL && work) {
         int cidx[8], pre[9];
         pre[0] = 0;
@@ -146,17 +146,18 @@ __global__ void __launch_bounds__(256, MC2D_SWEEPG_MIN_BLOCKS) k_sweep_g(SweepAr
             pre[q + 1] = pre[q] + a.cnt[cidx[q]];
         }
         M = pre[8];
-        staged = (M <= nb_cap);
-        if (staged) {
+        if (M <= nb_cap) {
+            Ms = M;
             for (int k = sl; k < M; k += G) {
                 int cc = cidx[0], cs = 0;
 #pragma unroll
                 for (int q = 1; q < 8; ++q)
                     if (k >= pre[q]) { cc = cidx[q]; cs = pre[q]; }
-                nbr[k] = to_local(a.pos[(size_t)cc * K + (k - cs)], x_lo, y_lo, g, hLx, hLy);
+                cand[k] = to_local(a.pos[(size_t)cc * K + (k - cs)], x_lo, y_lo, g, hLx, hLy);
             }
         }
     }
+    double2 *own = cand + Ms;
     if (work) {
         for (int s = sl; s < n_own; s += G) {
             own[s] = to_local(a.pos[(size_t)cell * K + s], x_lo, y_lo, g, hLx, hLy);
@@ -164,6 +165,8 @@ __global__ void __launch_bounds__(256, MC2D_SWEEPG_MIN_BLOCKS) k_sweep_g(SweepAr
         }
     }
     __syncwarp();
+    const int cap_idx = nb_cap + K - 1;  // last valid slot of this group's block (clamp for masked lanes)
+    const bool cold = (POT != POT_IDEAL) && __any_sync(FULL_MASK, M > Ms);  // some group reads neighbours from global
 
     double dU_total = 0.0;
     unsigned int c_att[3] = {0, 0, 0}, c_acc[3] = {0, 0, 0}, c_ovf = 0;
@@ -174,7 +177,8 @@ __global__ void __launch_bounds__(256, MC2D_SWEEPG_MIN_BLOCKS) k_sweep_g(SweepAr
     // ---- K2: displacement rounds (MC.cpp:96-123); one trial per group per round ----
     {
         const int T = warp_max_int(n_disp);
-        const int KM = warp_max_int(M + n_own);
+        const int KM = warp_max_int(Ms + n_own);
+        const int KC = cold ? warp_max_int(M - Ms) : 0;
         for (int t = 0; t < T; ++t) {
             if ((t & (G - 1)) == 0)  // sub-lane s draws the words of trial t + s of its cell's stream
                 batch = philox4x32_10(cell_gid, MC2D_TAG_DISP | (uint32_t)(t + sl), a.sweep_lo, a.sweep_hi, a.seed_lo,
@@ -192,15 +196,22 @@ __global__ void __launch_bounds__(256, MC2D_SWEEPG_MIN_BLOCKS) k_sweep_g(SweepAr
             double dE = 0.0;
             if (POT != POT_IDEAL) {
                 double acc = 0.0;
-                const int ntot = M + n_own, self = M + i;
-                for (int k = sl; k < KM; k += G) {
+                const int ntot = Ms + n_own, self = Ms + i;
+                for (int k = sl; k < KM; k += G) {  // hot loop: shared memory only
                     const bool valid = inside && k < ntot && k != self;
-                    double2 c;
-                    if (k >= M) c = own[min(k - M, K - 1)];
-                    else if (staged) c = nbr[k];
-                    else c = valid ? slow_candidate(a.pos, a.cnt, g.ghost, g.nx, g.ny, K, lcx, cy, k, x_lo, y_lo, g.Lx, g.Ly) : make_double2(0.0, 0.0);
+                    const double2 c = cand[min(k, cap_idx)];
                     acc += pair_e_sel<POT>(c.x - un.x, c.y - un.y, a.r2cut, a.pp, valid) -
                            pair_e_sel<POT>(c.x - uo.x, c.y - uo.y, a.r2cut, a.pp, valid);
+                }
+                if (cold) {
+                    for (int k = sl; k < KC; k += G) {
+                        const bool valid = inside && k < M - Ms;
+                        double2 c = make_double2(0.0, 0.0);
+                        if (valid)
+                            c = slow_candidate(a.pos, a.cnt, g.ghost, g.nx, g.ny, K, lcx, cy, k, x_lo, y_lo, g.Lx, g.Ly);
+                        acc += pair_e_sel<POT>(c.x - un.x, c.y - un.y, a.r2cut, a.pp, valid) -
+                               pair_e_sel<POT>(c.x - uo.x, c.y - uo.y, a.r2cut, a.pp, valid);
+                    }
                 }
                 dE = group_sum<G>(acc);
             }
@@ -235,7 +246,8 @@ __global__ void __launch_bounds__(256, MC2D_SWEEPG_MIN_BLOCKS) k_sweep_g(SweepAr
     // ---- K3: grand-canonical rounds (MC.cpp:189-249); insertion and deletion share one probe loop ----
     {
         const int T = warp_max_int(n_gc);
-        const int KM0 = warp_max_int(M + n_own);
+        const int KM0 = warp_max_int(Ms + n_own);
+        const int KC = cold ? warp_max_int(M - Ms) : 0;
         for (int t = 0; t < T; ++t) {
             if ((t & (G - 1)) == 0)
                 batch = philox4x32_10(cell_gid, MC2D_TAG_GC | (uint32_t)(t + sl), a.sweep_lo, a.sweep_hi, a.seed_lo,
@@ -259,15 +271,21 @@ __global__ void __launch_bounds__(256, MC2D_SWEEPG_MIN_BLOCKS) k_sweep_g(SweepAr
             double dE = 0.0;
             if (POT != POT_IDEAL) {
                 double acc = 0.0;
-                const int ntot = M + n_own, self = (kind == 2) ? M + i : -1;
+                const int ntot = Ms + n_own, self = (kind == 2) ? Ms + i : -1;
                 const int KM = KM0 + t;  // at most t insertions so far
                 for (int k = sl; k < KM; k += G) {
                     const bool valid = evaluate && k < ntot && k != self;
-                    double2 c;
-                    if (k >= M) c = own[min(k - M, K - 1)];
-                    else if (staged) c = nbr[k];
-                    else c = valid ? slow_candidate(a.pos, a.cnt, g.ghost, g.nx, g.ny, K, lcx, cy, k, x_lo, y_lo, g.Lx, g.Ly) : make_double2(0.0, 0.0);
+                    const double2 c = cand[min(k, cap_idx)];
                     acc += pair_e_sel<POT>(c.x - probe.x, c.y - probe.y, a.r2cut, a.pp, valid);
+                }
+                if (cold) {
+                    for (int k = sl; k < KC; k += G) {
+                        const bool valid = evaluate && k < M - Ms;
+                        double2 c = make_double2(0.0, 0.0);
+                        if (valid)
+                            c = slow_candidate(a.pos, a.cnt, g.ghost, g.nx, g.ny, K, lcx, cy, k, x_lo, y_lo, g.Lx, g.Ly);
+                        acc += pair_e_sel<POT>(c.x - probe.x, c.y - probe.y, a.r2cut, a.pp, valid);
+                    }
                 }
                 acc = group_sum<G>(acc);
                 dE = (kind == 2) ? -acc : acc;  // MC.cpp:200,225
