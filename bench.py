@@ -286,7 +286,7 @@ def main():
     alg_bytes = (32.0 * st_r["attempted"][0] + 20.0 * (st_r["attempted"][1] + st_r["attempted"][2])) / nl + 8.0 * cells_per_pass
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_sweep_g<LJ, G=4> (one colour pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_sweep_p<LJ, G=4> (one colour pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes, "ms_per_launch": k_ms,
                 "share_of_sweep_time": info.k_sweep_ms / max(info.last_sweep_ms, 1e-9),

@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmc2d.so")
 SOURCES = ["mc2d.cu"]
-HEADERS = ["mc2d_kernels.cuh", "sweep_kernel.cuh", "sweep_kernel_g.cuh", "group_kernels.cuh","pair_potentials.cuh", "philox.h", os.path.join("..", "..", "include", "mc2d.h")]
+HEADERS = ["mc2d_kernels.cuh", "sweep_kernel.cuh", "sweep_kernel_p.cuh", "group_kernels.cuh","pair_potentials.cuh", "philox.h", os.path.join("..", "..", "include", "mc2d.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

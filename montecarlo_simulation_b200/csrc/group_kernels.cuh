@@ -1,5 +1,5 @@
 // group_kernels.cuh — production variants of K4 (energy + virial) and K1' (re-bin) with G lanes per
-// cell and 32/G cells per warp (same reasoning as sweep_kernel_g.cuh: a 2.5-sigma LJ cell at
+// cell and 32/G cells per warp (same reasoning as sweep_kernel_p.cuh: a 2.5-sigma LJ cell at
 // rho = 0.5 has ~16 half-shell / ~28 full-shell candidates, which does not fill a warp; the per-cell
 // fixed cost — nine count loads, prefix, candidate decode — is shared by 32/G cells).
 // The warp-per-cell versions in mc2d_kernels.cuh remain for the per-particle parity hooks (PERP).
@@ -94,9 +94,16 @@ __global__ void __launch_bounds__(256) k_energy_virial_g(V v, PairParams pp, dou
 
 // K1', G lanes per new cell: gather from the 3x3 old cells by ballot compaction inside the group.
 // Same result (cell contents AND slot order) as k_rebin.
+//
+// The origin moves by (sdx, sdy) = new - old, each inside (-d, d): a new cell overlaps only the old
+// cell of the same index and its neighbour on the side the origin moved to, so 4 of the 9 old
+// cells can contribute.  The other 5 are skipped (their count is taken as 0) unless the shift along
+// that axis is smaller than the rounding slack `eps` of the cell assignment; skipping them does not
+// change the slot order because they contribute nothing.
 template <int G>
 __global__ void __launch_bounds__(256) k_rebin_g(const double2 *pos_o, const int *cnt_o, const int *ids_o,
-                                                 double2 *pos_n, int *cnt_n, int *ids_n, Grid gn, int *err) {
+                                                 double2 *pos_n, int *cnt_n, int *ids_n, Grid gn, double sdx,
+                                                 double sdy, int *err) {
     constexpr int GPW = 32 / G;
     const int lane = threadIdx.x & 31;
     const int gi = lane / G, sl = lane % G;
@@ -112,13 +119,16 @@ __global__ void __launch_bounds__(256) k_rebin_g(const double2 *pos_o, const int
     for (int c = 0; c < 9; ++c) {
         const int ddx = c / 3 - 1, ddy = c % 3 - 1;
         const bool dup = (gn.nx == 2 && ddx < 0) || (gn.ny == 2 && ddy < 0);
+        const double ex = 1e-9 * gn.dx, ey = 1e-9 * gn.dy;
+        const bool reach = (ddx == 0 || (sdx > ex ? ddx > 0 : (sdx < -ex ? ddx < 0 : true)) || gn.nx == 2) &&
+                           (ddy == 0 || (sdy > ey ? ddy > 0 : (sdy < -ey ? ddy < 0 : true)) || gn.ny == 2);
         int ocx = lcx + ddx, ocy = cy + ddy;
         if (!gn.ghost) {
             if (ocx < 0) ocx += gn.nx; else if (ocx >= gn.nx) ocx -= gn.nx;
         }
         if (ocy < 0) ocy += gn.ny; else if (ocy >= gn.ny) ocy -= gn.ny;
         tc[c] = ocx * gn.ny + ocy;
-        ts[c + 1] = ts[c] + ((has && !dup) ? cnt_o[tc[c]] : 0);
+        ts[c + 1] = ts[c] + ((has && !dup && reach) ? cnt_o[tc[c]] : 0);
     }
     const int M = ts[9];
     const int KM = warp_max_int(M);

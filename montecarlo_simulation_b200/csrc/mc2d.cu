@@ -118,6 +118,10 @@ struct mc2d_ctx {
     unsigned long long *d_pair_stats = nullptr;  // 2 + [2] particle count
     int *d_err = nullptr;                      // [0] overflow need, [1] flags, [2] max count
     DevBuf partial, trace_buf;
+    DevBuf order_buf;  // work order of k_sweep_p (k_order_local), rebuilt after every re-bin
+    bool order_valid = false;
+    int *d_work = nullptr;  // 4 work-item ticket counters (one per colour pass of a sweep)
+    int num_sms = 0;
     DevBuf xy_in, ids_in, keys, keys_sorted, idx, idx_sorted, spos, sids, start, cub_tmp, pts, excl, outE, outC,
         outI, offsets;
     unsigned long long *d_trace_n = nullptr;
@@ -127,7 +131,6 @@ struct mc2d_ctx {
     double last_sweep_ms = 0, last_energy_ms = 0;
     long long last_tests = 0, last_evals = 0;
     unsigned long long attr_set = 0;  // bitmask of k_sweep instantiations whose smem attribute is set
-    unsigned long long attr_set_g = 0;  // same for k_sweep_g
     long long n_last = 0;             // last known particle count (sizes the neighbour staging area)
     bool ktiming = false;
     std::vector<cudaEvent_t> kev;  // event pool for per-kernel timing
@@ -307,6 +310,8 @@ extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
     CU(cudaMalloc(&ctx->d_energy, 4 * sizeof(double)));
     CU(cudaMalloc(&ctx->d_pair_stats, 4 * sizeof(unsigned long long)));
     CU(cudaMalloc(&ctx->d_err, 4 * sizeof(int)));
+    CU(cudaMalloc(&ctx->d_work, 4 * sizeof(int)));
+    CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->dev));
     CU(cudaMalloc(&ctx->d_trace_n, sizeof(unsigned long long)));
     CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_energy, 0, 4 * sizeof(double), ctx->stream));
@@ -338,12 +343,13 @@ extern "C" int mc2d_destroy(mc2d_ctx *ctx) {
         free_slots(ctx);
         DevBuf *bufs[] = {&ctx->partial, &ctx->trace_buf, &ctx->xy_in, &ctx->ids_in, &ctx->keys, &ctx->keys_sorted,
                           &ctx->idx, &ctx->idx_sorted, &ctx->spos, &ctx->sids, &ctx->start, &ctx->cub_tmp, &ctx->pts,
-                          &ctx->excl, &ctx->outE, &ctx->outC, &ctx->outI, &ctx->offsets};
+                          &ctx->excl, &ctx->outE, &ctx->outC, &ctx->outI, &ctx->offsets, &ctx->order_buf};
         for (DevBuf *b : bufs) b->release();
         if (ctx->d_counters) cudaFree(ctx->d_counters);
         if (ctx->d_energy) cudaFree(ctx->d_energy);
         if (ctx->d_pair_stats) cudaFree(ctx->d_pair_stats);
         if (ctx->d_err) cudaFree(ctx->d_err);
+        if (ctx->d_work) cudaFree(ctx->d_work);
         if (ctx->d_trace_n) cudaFree(ctx->d_trace_n);
         if (ctx->ev0) cudaEventDestroy(ctx->ev0);
         if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -534,6 +540,7 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
                                                              ctx->d_err);
     ctx->launches++;
     ctx->have_particles = true;
+    ctx->order_valid = false;
     ctx->n_last = kept;
     // The sweep counter (part of every Philox counter) is NOT reset: a context that is re-uploaded
     // between batches (the end-to-end pattern: upload, sweep, download) must not replay the random
@@ -871,17 +878,6 @@ static int launch_sweep_kernel(mc2d_ctx *ctx, const SweepArgs &a, int nblocks, i
     return MC2D_OK;
 }
 
-template <int POT, int G, bool TRACE>
-static int launch_sweep_g(mc2d_ctx *ctx, const SweepArgs &a, int nblocks, int wpb, size_t smem, int nb_cap, int inst) {
-    if (!(ctx->attr_set_g & (1ull << inst))) {
-        CU(cudaFuncSetAttribute(k_sweep_g<POT, G, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        ctx->attr_set_g |= (1ull << inst);
-    }
-    k_sweep_g<POT, G, TRACE><<<nblocks, wpb * 32, smem, ctx->stream>>>(a, nb_cap);
-    ctx->launches++;
-    return MC2D_OK;
-}
-
 static int ktime_begin(mc2d_ctx *ctx, int kind) {
     if (!ctx->ktiming) return MC2D_OK;
     const size_t need = 2 * (ctx->kev_kind.size() + 1);
@@ -897,6 +893,43 @@ static int ktime_begin(mc2d_ctx *ctx, int kind) {
 static int ktime_end(mc2d_ctx *ctx) {
     if (!ctx->ktiming) return MC2D_OK;
     CU(cudaEventRecord(ctx->kev[2 * ctx->kev_kind.size() - 1], ctx->stream));
+    return MC2D_OK;
+}
+
+// per colour and column pair: active cells by falling (occupancy, candidates) -> ctx->order_buf
+static int build_order(mc2d_ctx *ctx) {
+    const Grid &g = ctx->g;
+    const int ncell = g.ncol * g.ny;
+    const size_t smem = sizeof(int) * (size_t)(3 * g.ny + g.ny / 2);
+    if (smem > 200 * 1024) FAIL(MC2D_ERR_GEOMETRY, "grid has %d rows: too many for k_order_local", g.ny);
+    static bool attr = false;
+    if (smem > 40 * 1024 && !attr) {
+        CU(cudaFuncSetAttribute(k_order_local, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    CU(ctx->order_buf.ensure(sizeof(int) * (size_t)ncell));
+    k_order_local<<<dim3(g.ncol / 2, 4), 256, smem, ctx->stream>>>(g, ctx->cnt[ctx->cur], ctx->order_buf.as<int>());
+    ctx->launches++;
+    ctx->order_valid = true;
+    return MC2D_OK;
+}
+
+template <int POT, int G, bool TRACE>
+static int launch_sweep_p(mc2d_ctx *ctx, const SweepArgs &a, int wpb, size_t smem, int nb_cap, int stride) {
+    static size_t smem_seen = (size_t)-1;  // per instantiation: resident CTAs per SM for this launch shape
+    static int wpb_seen = 0, occ = 0;
+    if (smem != smem_seen || wpb != wpb_seen) {
+        CU(cudaFuncSetAttribute(k_sweep_p<POT, G, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        int nb = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sweep_p<POT, G, TRACE>, wpb * 32, smem));
+        occ = std::max(1, nb);
+        smem_seen = smem;
+        wpb_seen = wpb;
+    }
+    const int want = (a.nitems + wpb - 1) / wpb;
+    const int grid = std::max(1, std::min(want, ctx->num_sms * occ));
+    k_sweep_p<POT, G, TRACE><<<grid, wpb * 32, smem, ctx->stream>>>(a, nb_cap, stride);
+    ctx->launches++;
     return MC2D_OK;
 }
 
@@ -917,42 +950,68 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
     if (per_warp * wpb > 200 * 1024) FAIL(MC2D_ERR_CELL_OVERFLOW, "cell capacity %d needs too much shared memory", K);
     const int nact = (g.ncol / 2) * (g.ny / 2);
-    // Kernel choice: G lanes per cell (k_sweep_g) unless the grid needs the per-pair minimum image.
-    // G follows the expected number of candidates per cell (9 cells x mean occupancy): 8 lanes for
-    // LJ-like neighbourhoods (~28 candidates), 4 for short-range ones (~6).  MC2D_SWEEP_G overrides
-    // (0 = one warp per cell), for tuning.
+    // Kernel choice: k_sweep_p (G lanes per cell, persistent warps over the sorted work list) unless the
+    // grid needs the per-pair minimum image or the cells are too big for its shared-memory layout; then
+    // k_sweep (one warp per cell).  G follows the expected number of candidates per cell (9 cells x mean
+    // occupancy): measured on config #4 (28 candidates), G = 4 beats 8 and 2; denser neighbourhoods
+    // (> 64 candidates) fill 8 lanes.  MC2D_SWEEP_G overrides (0 = k_sweep), for tuning and tests.
     int G = 0, nb_cap = 0;
-    size_t per_group = 0;
-    if (!minimg) {
+    size_t per_group = 0;  // bytes between the candidate arrays of two groups
+    if (!minimg && K <= 255) {
         const double n_c = (double)std::max<long long>(ctx->n_last, 1) / std::max(1, g.ncol * g.ny);
-        // measured on config #4 (28 candidates per cell), 20 sweeps: G=4 7.8 ms, G=8 9.1 ms, G=16 14.8 ms,
-        // one warp per cell 13.6 ms; denser neighbourhoods (> 64 candidates) fill 8 lanes better
         G = (9.0 * n_c > 64.0) ? 8 : 4;
         if (const char *e = getenv("MC2D_SWEEP_G")) G = atoi(e);
-        if (G != 0 && G != 2 && G != 4 && G != 8 && G != 16)
-            FAIL(MC2D_ERR_INVALID, "MC2D_SWEEP_G must be 0, 2, 4, 8 or 16");
-        nb_cap = ideal ? 0 : std::min(8 * K, even_up((int)(8.0 * n_c * 1.6 + 12.0), 4));
-        per_group = (size_t)(nb_cap + K) * sizeof(double2) + (ctx->use_ids ? (size_t)K * sizeof(int) : 0);
+        if (G != 0 && G != 4 && G != 8) FAIL(MC2D_ERR_INVALID, "MC2D_SWEEP_G must be 0, 4 or 8");
         if (G) {
-            wpb = 8;
-            while (wpb > 2 && per_group * (32 / G) * wpb > 72 * 1024) wpb >>= 1;  // keep >= 3 CTAs per SM
-            if (per_group * (32 / G) * wpb > 200 * 1024) G = 0;  // very large cells: one warp per cell
+            // A quarter warp (8 lanes x 16 B) must touch 32 distinct banks: the groups inside it sit
+            // G*16 bytes apart modulo 128 (profiles/r01f: an unpadded stride doubled every LDS.128).
+            const size_t resid = (size_t)(G * 16) % 128;
+            auto stride_of = [&](int nb) {
+                const size_t b = (size_t)(nb + K) * sizeof(double2) + (ctx->use_ids ? (size_t)K * sizeof(int) : 0);
+                size_t st = b / 128 * 128 + resid;
+                return st < b ? st + 128 : st;
+            };
+            const int nb_want = ideal ? 0 : std::min(8 * K, even_up((int)(8.0 * n_c * 1.6 + 12.0), 4));
+            const int nb_min = ideal ? 0 : std::min(8 * K, even_up((int)(8.0 * n_c * 1.25 + 8.0), 4));
+            // largest neighbour capacity that leaves 24 warps per SM (9 KB of shared memory per warp)
+            int w0 = 8;
+            if (const char *e = getenv("MC2D_SWEEP_WPB")) w0 = std::max(1, std::min(8, atoi(e)));  // tuning
+            const size_t warp_budget = 72 * 1024 / 8;
+            bool found = false;
+            for (int nb = nb_want; nb >= nb_min && !found; nb -= 4)
+                if (stride_of(nb) * (32 / G) <= warp_budget) {
+                    wpb = w0;
+                    nb_cap = nb;
+                    found = true;
+                }
+            if (!found) {  // big cells: fewer warps per SM, then one warp per cell
+                nb_cap = nb_want;
+                wpb = w0;
+                while (wpb > 1 && stride_of(nb_cap) * (32 / G) * wpb > 200 * 1024) wpb >>= 1;
+                if (stride_of(nb_cap) * (32 / G) * wpb > 200 * 1024) G = 0;
+            }
+            per_group = stride_of(nb_cap);
         }
     }
     if (!G) {
         wpb = 8;
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
     }
+    const bool persistent = G != 0;
     const int cells_per_block = G ? wpb * (32 / G) : wpb;
-    const int nblocks = std::max(1, (nact + cells_per_block - 1) / cells_per_block);
+    // k_sweep_p: a work item = 32/G cells of one column pair; k_sweep: one CTA per cells_per_block
+    const int nitems = G ? (g.ncol / 2) * ((g.ny / 2 + 32 / G - 1) / (32 / G)) : 0;
+    const int nblocks = persistent ? nitems : std::max(1, (nact + cells_per_block - 1) / cells_per_block);
     CU(ctx->partial.ensure(sizeof(double) * 4 * (size_t)nblocks));
-    // per-CTA dU accumulators live across the whole batch and are reduced once at its end
+    // per-CTA (per-item) dU accumulators live across the whole batch and are reduced once at its end
     CU(cudaMemsetAsync(ctx->partial.p, 0, sizeof(double) * 4 * (size_t)nblocks, ctx->stream));
     if (trace) {
         CU(ctx->trace_buf.ensure(sizeof(mc2d_trial) * (size_t)trace_cap));
         CU(cudaMemsetAsync(ctx->d_trace_n, 0, sizeof(unsigned long long), ctx->stream));
     }
     const int ncell_owned = g.ncol * g.ny;
+    int rebin_G = 4;
+    if (const char *e = getenv("MC2D_REBIN_G")) rebin_G = atoi(e);
     ctx->kev_kind.clear();
     CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -966,10 +1025,14 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             gn.oy = sy;
             const int nb = 1 - ctx->cur;
             if (int rc = ktime_begin(ctx, 1)) return rc;
-            if (K <= 64)  // 8 lanes per new cell, 4 cells per warp
+            if (K <= 64 && rebin_G == 4)  // 4 lanes per new cell, 8 cells per warp
+                k_rebin_g<4><<<(ncell_owned + 63) / 64, 256, 0, ctx->stream>>>(
+                    ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->use_ids ? ctx->ids[ctx->cur] : nullptr, ctx->pos[nb],
+                    ctx->cnt[nb], ctx->use_ids ? ctx->ids[nb] : nullptr, gn, gn.ox - g.ox, gn.oy - g.oy, ctx->d_err);
+            else if (K <= 64)  // 8 lanes per new cell, 4 cells per warp
                 k_rebin_g<8><<<(ncell_owned + 31) / 32, 256, 0, ctx->stream>>>(
                     ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->use_ids ? ctx->ids[ctx->cur] : nullptr, ctx->pos[nb],
-                    ctx->cnt[nb], ctx->use_ids ? ctx->ids[nb] : nullptr, gn, ctx->d_err);
+                    ctx->cnt[nb], ctx->use_ids ? ctx->ids[nb] : nullptr, gn, gn.ox - g.ox, gn.oy - g.oy, ctx->d_err);
             else  // very populated cells: one warp per new cell
                 k_rebin<<<(ncell_owned + 7) / 8, 256, 0, ctx->stream>>>(
                     ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->use_ids ? ctx->ids[ctx->cur] : nullptr, ctx->pos[nb],
@@ -978,14 +1041,23 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             ctx->launches++;
             ctx->cur = nb;
             g = gn;
+            ctx->order_valid = false;
             int rc = halo_exchange(ctx, ctx->cur, true, true);
             if (rc) return rc;
+        }
+        if (persistent) {
+            if (!ctx->order_valid)
+                if (int rc = build_order(ctx)) return rc;
+            CU(cudaMemsetAsync(ctx->d_work, 0, 4 * sizeof(int), ctx->stream));
         }
         for (int p = 0; p < 4; ++p) {
             SweepArgs a;
             a.pos = ctx->pos[ctx->cur];
             a.cnt = ctx->cnt[ctx->cur];
             a.ids = ctx->use_ids ? ctx->ids[ctx->cur] : nullptr;
+            a.order = persistent ? ctx->order_buf.as<int>() : nullptr;
+            a.work = ctx->d_work + p;
+            a.nitems = nitems;
             a.g = g;
             a.pp = ctx->pp;
             a.r2cut = ctx->r2cut;
@@ -1014,19 +1086,14 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             const int pot = ctx->prm.potential;
             DISPATCH_POT(pot, {
                 const int inst = POT * 4 + (minimg ? 2 : 0) + (trace ? 1 : 0);
-                const int inst_g = POT * 8 + (G == 2 ? 0 : G == 4 ? 2 : G == 8 ? 4 : 6) + (trace ? 1 : 0);
-                if (G == 2) {
-                    if (trace) rc = launch_sweep_g<POT, 2, true>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
-                    else rc = launch_sweep_g<POT, 2, false>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
-                } else if (G == 4) {
-                    if (trace) rc = launch_sweep_g<POT, 4, true>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
-                    else rc = launch_sweep_g<POT, 4, false>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
-                } else if (G == 8) {
-                    if (trace) rc = launch_sweep_g<POT, 8, true>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
-                    else rc = launch_sweep_g<POT, 8, false>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
-                } else if (G == 16) {
-                    if (trace) rc = launch_sweep_g<POT, 16, true>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
-                    else rc = launch_sweep_g<POT, 16, false>(ctx, a, nblocks, wpb, smem, nb_cap, inst_g);
+                if (persistent) {
+                    if (G == 4) {
+                        if (trace) rc = launch_sweep_p<POT, 4, true>(ctx, a, wpb, smem, nb_cap, (int)per_group);
+                        else rc = launch_sweep_p<POT, 4, false>(ctx, a, wpb, smem, nb_cap, (int)per_group);
+                    } else {
+                        if (trace) rc = launch_sweep_p<POT, 8, true>(ctx, a, wpb, smem, nb_cap, (int)per_group);
+                        else rc = launch_sweep_p<POT, 8, false>(ctx, a, wpb, smem, nb_cap, (int)per_group);
+                    }
                 } else if (trace) {
                     if (minimg) rc = launch_sweep_kernel<POT, true, true>(ctx, a, nblocks, wpb, smem, inst);
                     else rc = launch_sweep_kernel<POT, false, true>(ctx, a, nblocks, wpb, smem, inst);

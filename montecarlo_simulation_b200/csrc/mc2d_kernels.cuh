@@ -600,5 +600,5 @@ __global__ void k_sum_counts(const int *cnt, int cell0, int ncell, unsigned long
 
 
 #include "sweep_kernel.cuh"
-#include "sweep_kernel_g.cuh"
+#include "sweep_kernel_p.cuh"
 #include "group_kernels.cuh"

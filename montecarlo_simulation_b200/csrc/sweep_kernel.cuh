@@ -24,6 +24,9 @@ struct SweepArgs {
     double2 *pos;
     int *cnt;
     int *ids;
+    const int *order;  // k_sweep_p: perm[colour][column pair][rank] (k_order_local)
+    int *work;         // k_sweep_p: work-item ticket counter of this pass
+    int nitems;        // k_sweep_p: work items per pass
     Grid g;
     PairParams pp;
     double r2cut, beta, zA, delta;

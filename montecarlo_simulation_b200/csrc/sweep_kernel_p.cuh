@@ -1,0 +1,562 @@
+// sweep_kernel_p.cuh — K2 + K3, production variant: persistent warps over a sorted work list.
+//
+// Same trial algorithm and Philox streams (keyed by global cell id and trial index) as k_sweep
+// (sweep_kernel.cuh, one warp per cell): the two give the same configurations (tested).  What
+// changes is the work decomposition — G lanes per cell, 32/G cells per warp — and the scheduling
+// (profiles/r01_notes.md):
+//
+//  * k_order_local sorts, per colour and per pair of cell columns, the active cells by falling
+//    (occupancy, candidate count).  A work item is 32/G consecutive cells of that order, so the
+//    32/G groups of a warp run the same number of displacement rounds and candidate iterations
+//    (in grid order a warp ran max-of-8 Poisson rounds: half of the lanes idle).
+//  * Items are numbered heavy-first (rank-major over the column pairs) and handed out through one
+//    atomic counter per pass to 148 x 3 resident CTAs: no CTA-launch / CTA-tail cost per item, and
+//    the warps of an SM drift out of phase, so the global-memory latency of one warp's staging
+//    hides behind the arithmetic of the others.
+//  * The index chain of an item (work ticket -> sorted cell -> 9 cell counts) is prefetched into
+//    registers while the previous items run: staging starts with the position loads.
+//
+// The energy change of a pass is accumulated per ITEM (fixed composition, fixed order inside the
+// warp), so the running energy stays reproducible although items are scheduled dynamically.
+#pragma once
+
+// ------------------------------------------------------------------------------------------------
+// k_order_local: grid (column pairs, 4 colours), 256 threads.  perm[colour][pair][j] = row index acy
+// of the j-th cell of that colour in that column pair, by falling (n_own, n_own + neighbours).
+// Stable counting sort: every rank depends only on the counts, never on timing.
+// ------------------------------------------------------------------------------------------------
+constexpr int ORDL_NB = 24;  // occupancy bins (23 and above share the first)
+constexpr int ORDL_MB = 16;  // candidate-count bins of width 4 (60 and above share the first)
+constexpr int ORDL_BINS = ORDL_NB * ORDL_MB;
+
+// dynamic shared memory: 3 columns x ny counts, then nay packed (bin << 16 | rank in warp)
+__global__ void __launch_bounds__(256) k_order_local(Grid g, const int *cnt, int *perm) {
+    extern __shared__ int ol_smem[];
+    __shared__ int wc[8][ORDL_BINS];
+    __shared__ int bin_base[ORDL_BINS];
+    const int p = blockIdx.x, colour = blockIdx.y;
+    const int px = colour & 1, py = colour >> 1;
+    const int nay = g.ny >> 1, npairs = g.ncol >> 1;
+    const int lcx = g.ghost + 2 * p + px;
+    int *ol_cnt = ol_smem, *ol_key = ol_smem + 3 * g.ny;
+    for (int i = threadIdx.x; i < 3 * g.ny; i += 256) {
+        const int c = i / g.ny, cy = i - c * g.ny;
+        int col = lcx + c - 1;
+        if (!g.ghost) {
+            if (col < 0) col += g.nx; else if (col >= g.nx) col -= g.nx;
+        }
+        ol_cnt[i] = cnt[col * g.ny + cy];
+    }
+    for (int i = threadIdx.x; i < 8 * ORDL_BINS; i += 256) (&wc[0][0])[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int per_warp = (nay + 7) / 8;  // each warp owns a contiguous range of rows (stable order)
+    for (int k0 = 0; k0 < per_warp; k0 += 32) {
+        const int k = k0 + lane;
+        const int acy = wib * per_warp + k;
+        const bool has = k < per_warp && acy < nay;
+        int b = ORDL_BINS;  // lanes without a cell match among themselves and are ignored
+        if (has) {
+            const int cy = 2 * acy + py;
+            const int ym = (cy == 0) ? g.ny - 1 : cy - 1, yp = (cy == g.ny - 1) ? 0 : cy + 1;
+            const int n = ol_cnt[g.ny + cy];
+            const int m = ol_cnt[ym] + ol_cnt[cy] + ol_cnt[yp] + ol_cnt[g.ny + ym] + ol_cnt[g.ny + yp] +
+                          ol_cnt[2 * g.ny + ym] + ol_cnt[2 * g.ny + cy] + ol_cnt[2 * g.ny + yp] + n;
+            b = (ORDL_NB - 1 - min(n, ORDL_NB - 1)) * ORDL_MB + (ORDL_MB - 1 - min(m >> 2, ORDL_MB - 1));
+        }
+        const unsigned peers = __match_any_sync(FULL_MASK, b);
+        const int r = __popc(peers & lt);
+        int prev = 0;
+        if (has) prev = wc[wib][b];
+        __syncwarp();
+        if (has && r == 0) wc[wib][b] = prev + __popc(peers);
+        __syncwarp();
+        if (has) ol_key[acy] = (b << 16) | (prev + r);
+    }
+    __syncthreads();
+    // per bin: exclusive prefix over the 8 warps, bin total -> bin_base
+    for (int b = threadIdx.x; b < ORDL_BINS; b += 256) {
+        int run = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int v = wc[w][b];
+            wc[w][b] = run;
+            run += v;
+        }
+        bin_base[b] = run;
+    }
+    __syncthreads();
+    if (wib == 0) {  // exclusive scan of the bin totals by one warp
+        constexpr int PER = ORDL_BINS / 32;
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) s += bin_base[lane * PER + i];
+        int incl = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= d) incl += t;
+        }
+        int run = incl - s;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int v = bin_base[lane * PER + i];
+            bin_base[lane * PER + i] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    int *out = perm + ((size_t)colour * npairs + p) * nay;
+    for (int k0 = 0; k0 < per_warp; k0 += 32) {
+        const int k = k0 + lane;
+        const int acy = wib * per_warp + k;
+        if (k < per_warp && acy < nay) {
+            const int key = ol_key[acy], b = key >> 16;
+            out[bin_base[b] + wc[wib][b] + (key & 0xffff)] = acy;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_sweep_p
+// ------------------------------------------------------------------------------------------------
+// absolute position -> coordinates relative to the cell origin (x_lo, y_lo), nearest periodic image
+__device__ __forceinline__ double2 to_local(double2 p, double x_lo, double y_lo, const Grid &g, double hLx,
+                                            double hLy) {
+    double ux = p.x - x_lo, uy = p.y - y_lo;
+    if (ux < -hLx) ux += g.Lx; else if (ux >= hLx) ux -= g.Lx;
+    if (uy < -hLy) uy += g.Ly; else if (uy >= hLy) uy -= g.Ly;
+    return make_double2(ux, uy);
+}
+
+// candidate k of a cell whose neighbours did not fit in shared memory: walk the 8 cells.
+// Scalar arguments only: taking the address of the kernel parameter struct would force a copy of it
+// to the local stack in every thread.
+__device__ __noinline__ double2 slow_candidate(const double2 *pos, const int *cnt, int ghost, int nx, int ny, int K,
+                                               int lcx, int cy, int k, double x_lo, double y_lo, double Lx,
+                                               double Ly) {
+    for (int q = 0; q < 8; ++q) {
+        const int o = q + (q >= 4);
+        int ncx = lcx + o / 3 - 1, ncy = cy + o % 3 - 1;
+        if (!ghost) {
+            if (ncx < 0) ncx += nx; else if (ncx >= nx) ncx -= nx;
+        }
+        if (ncy < 0) ncy += ny; else if (ncy >= ny) ncy -= ny;
+        const int c = ncx * ny + ncy;
+        const int n = cnt[c];
+        if (k < n) {
+            const double2 p = pos[(size_t)c * K + k];
+            double ux = p.x - x_lo, uy = p.y - y_lo;
+            if (ux < -0.5 * Lx) ux += Lx; else if (ux >= 0.5 * Lx) ux -= Lx;
+            if (uy < -0.5 * Ly) uy += Ly; else if (uy >= 0.5 * Ly) uy -= Ly;
+            return make_double2(ux, uy);
+        }
+        k -= n;
+    }
+    return make_double2(1e300, 1e300);
+}
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) v += __shfl_xor_sync(FULL_MASK, v, d);
+    return v;
+}
+__device__ __forceinline__ int warp_max_int(int v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(FULL_MASK, v, d));
+    return v;
+}
+
+#ifndef MC2D_SWEEPP_MIN_BLOCKS
+#define MC2D_SWEEPP_MIN_BLOCKS 3
+#endif
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// 1/x from the hardware seed (rcp.approx.ftz.f64, relative error <= 2^-23) and ONE Newton step:
+// relative error <= 2^-46 = 1.4e-14, four orders below the 1e-10 bound on per-trial dE
+// (tests/test_gpu_parity.py::test_per_trial_dE_matches_oracle); the parity hooks K4/K6 keep the
+// IEEE division of the reference.
+__device__ __forceinline__ double rcp_newton1(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return fma(r, fma(-x, r, 1.0), r);
+}
+
+// Empty candidate slots hold this point: its distance to anything in a cell is ~1e150, beyond every
+// cutoff, so the hot loop needs no bounds test.
+#define MC2D_FAR 1e150
+
+// One pair term t with u(r) = pair_scale<POT>() * t, zero beyond the inclusive cutoff (cell_list.cpp:62)
+// and for the excluded (self) slot.  LJ: t = r^-12 - r^-6 with the mask applied to the HIGH WORD of r^2
+// (masked pairs get r^2 ~ 1e300, whose r^-6 underflows to 0): one predicate, one select, no branch.
+template <int POT>
+__device__ __forceinline__ double pair_term(double dx, double dy, double r2cut, const PairParams &pp, bool notself) {
+    const double r2 = fma(dx, dx, dy * dy);
+    if (POT == POT_LJ || POT == POT_WCA) {
+        bool ok = notself && r2 <= r2cut;
+        if (POT == POT_WCA) ok = ok && r2 < 1.2599;  // potential.cpp:62
+        const double r2m = __hiloint2double(ok ? __double2hiint(r2) : 0x7E37E43C, __double2loint(r2));
+        const double ri = rcp_newton1(r2m);
+        const double r6 = ri * ri * ri;
+        const double t = fma(r6, r6, -r6);
+        return (POT == POT_WCA) ? t + (ok ? 0.25 : 0.0) : t;
+    } else {
+        return (notself && r2 <= r2cut) ? pair_u<POT>(r2, pp) : 0.0;
+    }
+}
+template <int POT>
+__device__ __forceinline__ double pair_scale() {
+    return (POT == POT_LJ || POT == POT_WCA) ? 4.0 : 1.0;
+}
+
+struct ItemMeta {
+    int acy;              // row index of the cell inside its colour (from perm), -1: no cell
+    int n_own;
+    uint32_t c_lo, c_hi;  // the 8 neighbour counts, one byte each (K <= 255)
+};
+
+// stored index of the 3x3 neighbourhood of stored cell (lcx, cy): col3[0..2] + row3[0..2]
+__device__ __forceinline__ void nbr_rows_cols(const Grid &g, int lcx, int cy, int col3[3], int row3[3]) {
+    int cm = lcx - 1, cp = lcx + 1;
+    if (!g.ghost) {
+        if (cm < 0) cm += g.nx;
+        if (cp >= g.nx) cp -= g.nx;
+    }
+    col3[0] = cm * g.ny; col3[1] = lcx * g.ny; col3[2] = cp * g.ny;
+    row3[0] = (cy == 0) ? g.ny - 1 : cy - 1; row3[1] = cy; row3[2] = (cy == g.ny - 1) ? 0 : cy + 1;
+}
+
+template <int POT, int G, bool TRACE>
+__global__ void __launch_bounds__(256, MC2D_SWEEPP_MIN_BLOCKS) k_sweep_p(SweepArgs a, int nb_cap, int stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned int cred[8][7];
+    constexpr int GPW = 32 / G;
+    const Grid &g = a.g;
+    const int K = g.K;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int gi = lane / G, sl = lane % G;
+    const int cap = nb_cap + K;  // candidate slots of one group
+    // `stride` bytes between groups: the host pads it so that a quarter warp reads 32 distinct banks
+    double2 *cand = reinterpret_cast<double2 *>(smem_raw + (size_t)(wib * GPW + gi) * stride);
+    int *own_id = reinterpret_cast<int *>(cand + cap);
+
+    const int nay = g.ny >> 1, npairs = g.ncol >> 1;
+    const int px = a.colour & 1, py = a.colour >> 1;
+    const int *perm = a.order + (size_t)a.colour * npairs * nay;
+    const double hLx = 0.5 * g.Lx, hLy = 0.5 * g.Ly;
+    const int src_base = gi * G;
+    const double2 far2 = make_double2(MC2D_FAR, MC2D_FAR);
+    const double escale = pair_scale<POT>();
+
+    unsigned int c_att[3] = {0, 0, 0}, c_acc[3] = {0, 0, 0}, c_ovf = 0;
+
+    // ---- the prefetch pipeline: ticket 3 items ahead, sorted cell 2 ahead, counts 1 ahead ----
+    // The first two items of a warp are fixed (warp w takes items w and W + w of the heavy-first list; the
+    // ticket counter hands out 2W, 2W + 1, ...): thousands of warps asking one address for their first
+    // ticket at the same instant would queue for tens of microseconds.
+    const int W = gridDim.x * wpb;
+    auto ticket = [&]() {
+        int v = 0;
+        if (lane == 0) v = 2 * W + atomicAdd(a.work, 1);
+        return v;
+    };
+    auto load_perm = [&](int item) {  // -> acy of this group's cell in `item`, or -1
+        const int p = item % npairs, j = (item / npairs) * GPW + gi;
+        return (item < a.nitems && j < nay) ? perm[(size_t)p * nay + j] : -1;
+    };
+    auto load_counts = [&](int item, int acy) {
+        ItemMeta m;
+        m.acy = acy;
+        m.n_own = 0;
+        m.c_lo = m.c_hi = 0;
+        if (acy >= 0) {
+            int col3[3], row3[3];
+            nbr_rows_cols(g, g.ghost + 2 * (item % npairs) + px, 2 * acy + py, col3, row3);
+            m.n_own = a.cnt[col3[1] + row3[1]];
+            if (POT != POT_IDEAL) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int o = q + (q >= 4);
+                    const uint32_t n = (uint32_t)a.cnt[col3[o / 3] + row3[o % 3]];
+                    if (q < 4) m.c_lo |= n << (8 * q);
+                    else m.c_hi |= n << (8 * (q - 4));
+                }
+            }
+        }
+        return m;
+    };
+    int it0 = blockIdx.x * wpb + wib;
+    int it1 = W + it0;
+    int it2 = __shfl_sync(FULL_MASK, ticket(), 0);
+    int acy1 = load_perm(it1);
+    ItemMeta m0 = load_counts(it0, load_perm(it0));
+
+    while (it0 < a.nitems) {
+        // issue the prefetches of the following items (consumed at the bottom of this iteration)
+        const int tick = ticket();
+        const int acy2 = load_perm(it2);
+        const ItemMeta m1 = load_counts(it1, acy1);
+
+        const bool has_cell = m0.acy >= 0;
+        const int acx = it0 % npairs;
+        const int lcx = g.ghost + 2 * acx + px, cy = 2 * max(m0.acy, 0) + py, gcx = g.col0 + 2 * acx + px;
+        const int cell = lcx * g.ny + cy;
+        const uint32_t cell_gid = (uint32_t)(gcx * g.ny + cy);
+        const double x_lo = g.ox + gcx * g.dx, y_lo = g.oy + cy * g.dy;
+        int n_own = m0.n_own;
+        const int n_disp = n_own > 0 ? (a.disp_cell > 0 ? a.disp_cell : a.disp_mult * n_own) : 0;
+        const int n_gc = has_cell ? a.n_gc : 0;
+        const bool work = (n_disp > 0 || n_gc > 0);
+
+        // ---- stage: 8 neighbour cells -> cand[0..Ms), own cell -> cand[Ms..Ms+n_own), raw copies by
+        //      cp.async (no registers, all in flight together: one exposed memory latency per item) ----
+        int M = 0, Ms = 0;
+        if (POT != POT_IDEAL && work) {
+            M = (int)__dp4a(m0.c_lo, 0x01010101u, __dp4a(m0.c_hi, 0x01010101u, 0u));
+            if (M <= nb_cap) Ms = M;
+        }
+        double2 *own = cand + Ms;
+        if (work) {
+            for (int s = sl; s < n_own; s += G) {
+                cp_async16(&own[s], &a.pos[(size_t)cell * K + s]);
+                if (a.ids) own_id[s] = a.ids[(size_t)cell * K + s];
+            }
+            if (Ms > 0) {  // lane sl copies neighbour cells sl, sl + G, ...
+                int col3[3], row3[3];
+                nbr_rows_cols(g, lcx, cy, col3, row3);
+                for (int q = sl; q < 8; q += G) {
+                    const int sh = 8 * (q & 3);
+                    const uint32_t below = (1u << sh) - 1u;  // bytes of the cells before q in their word
+                    const int n = (int)(((q < 4 ? m0.c_lo : m0.c_hi) >> sh) & 255u);
+                    const int pre = (q < 4) ? (int)__dp4a(m0.c_lo & below, 0x01010101u, 0u)
+                                            : (int)__dp4a(m0.c_hi & below, 0x01010101u, __dp4a(m0.c_lo, 0x01010101u, 0u));
+                    const int o = q + (q >= 4), oc = (o * 11) >> 5, orow = o - 3 * oc;
+                    const int cb = oc == 0 ? col3[0] : (oc == 1 ? col3[1] : col3[2]);
+                    const int rb = orow == 0 ? row3[0] : (orow == 1 ? row3[1] : row3[2]);
+                    const double2 *src = a.pos + (size_t)(cb + rb) * K;
+                    for (int s = 0; s < n; ++s) cp_async16(&cand[pre + s], &src[s]);
+                }
+            }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        const int ntot0 = Ms + n_own;
+        const int KM0 = warp_max_int(ntot0);  // candidate iterations of this item (all groups in lock step)
+        if (work) {  // to cell-local coordinates in place, then far points behind the list
+            for (int k = sl; k < ntot0; k += G) cand[k] = to_local(cand[k], x_lo, y_lo, g, hLx, hLy);
+            const int fill_to = min(KM0 + a.n_gc, cap);
+            for (int k = ntot0 + sl; k < fill_to; k += G) cand[k] = far2;
+        }
+        __syncwarp();
+        const bool cold = (POT != POT_IDEAL) && __any_sync(FULL_MASK, M > Ms);
+
+        double dU_total = 0.0;
+        bool dirty = false;
+        Philox4 batch = {0u, 0u, 0u, 0u};
+
+        // ---- K2: displacement rounds (MC.cpp:96-123); one trial per group per round ----
+        {
+            const int T = warp_max_int(n_disp);
+            const int KC = cold ? warp_max_int(M - Ms) : 0;
+            for (int t = 0; t < T; ++t) {
+                if ((t & (G - 1)) == 0)  // sub-lane s draws the words of trial t + s of its cell's stream
+                    batch = philox4x32_10(cell_gid, MC2D_TAG_DISP | (uint32_t)(t + sl), a.sweep_lo, a.sweep_hi,
+                                          a.seed_lo, a.seed_hi);
+                const int src = src_base + (t & (G - 1));
+                const uint32_t rx = __shfl_sync(FULL_MASK, batch.x, src), ry = __shfl_sync(FULL_MASK, batch.y, src);
+                const uint32_t rz = __shfl_sync(FULL_MASK, batch.z, src), rw = __shfl_sync(FULL_MASK, batch.w, src);
+                const bool act = t < n_disp;
+                const int i = act ? (int)__umulhi(rx, (uint32_t)n_own) : 0;
+                const double2 uo = act ? own[i] : make_double2(0.0, 0.0);
+                double2 un;
+                un.x = uo.x + a.delta * (2.0 * mc2d_u01(ry) - 1.0);
+                un.y = uo.y + a.delta * (2.0 * mc2d_u01(rz) - 1.0);
+                const bool inside = act && (un.x >= 0.0 && un.x < g.dx && un.y >= 0.0 && un.y < g.dy);
+                double dE = 0.0;
+                if (POT != POT_IDEAL) {
+                    double acc = 0.0;
+                    const int self = Ms + i;
+                    // hot loop: shared memory only; slots behind a group's list hold far points
+#pragma unroll 2
+                    for (int k = sl; k < KM0; k += G) {
+                        const double2 c = cand[k];
+                        const bool notself = k != self;
+                        acc += pair_term<POT>(c.x - un.x, c.y - un.y, a.r2cut, a.pp, notself) -
+                               pair_term<POT>(c.x - uo.x, c.y - uo.y, a.r2cut, a.pp, notself);
+                    }
+                    if (cold) {
+                        for (int k = sl; k < KC; k += G) {
+                            double2 c = far2;
+                            if (inside && k < M - Ms)
+                                c = slow_candidate(a.pos, a.cnt, g.ghost, g.nx, g.ny, K, lcx, cy, k, x_lo, y_lo, g.Lx,
+                                                   g.Ly);
+                            acc += pair_term<POT>(c.x - un.x, c.y - un.y, a.r2cut, a.pp, true) -
+                                   pair_term<POT>(c.x - uo.x, c.y - uo.y, a.r2cut, a.pp, true);
+                        }
+                    }
+                    dE = escale * group_sum<G>(acc);
+                }
+                bool accept = inside && (dE <= 0.0);
+                if (__any_sync(FULL_MASK, inside && dE > 0.0))
+                    accept = accept || (inside && mc2d_u01(rw) < exp(-a.beta * dE));  // MC.cpp:110-115
+                if (accept && sl == 0) own[i] = un;
+                if (sl == 0) {
+                    c_att[0] += act;
+                    c_acc[0] += accept;
+                    if (accept) dU_total += dE;
+                }
+                dirty = dirty || accept;
+                if (TRACE && sl == 0 && act) {
+                    unsigned long long slot = atomicAdd(a.trace_n, 1ull);
+                    if ((long long)slot < a.trace_cap) {
+                        mc2d_trial tr;
+                        tr.pass = a.pass; tr.cell = (int)cell_gid; tr.seq = t; tr.kind = 0;
+                        tr.accepted = accept ? 1 : 0; tr.reserved = inside ? 1 : 0;
+                        double ox_ = x_lo + uo.x, oy_ = y_lo + uo.y, nx_ = x_lo + un.x, ny_ = y_lo + un.y;
+                        if (ox_ >= g.Lx) ox_ -= g.Lx; if (oy_ >= g.Ly) oy_ -= g.Ly;
+                        if (nx_ >= g.Lx) nx_ -= g.Lx; if (ny_ >= g.Ly) ny_ -= g.Ly;
+                        tr.old_x = ox_; tr.old_y = oy_; tr.new_x = nx_; tr.new_y = ny_;
+                        tr.dE = inside ? dE : nan("");
+                        a.trace[slot] = tr;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- K3: grand-canonical rounds (MC.cpp:189-249); insertion and deletion share one probe loop ----
+        {
+            const int T = warp_max_int(n_gc);
+            const int KC = cold ? warp_max_int(M - Ms) : 0;
+            for (int t = 0; t < T; ++t) {
+                if ((t & (G - 1)) == 0)
+                    batch = philox4x32_10(cell_gid, MC2D_TAG_GC | (uint32_t)(t + sl), a.sweep_lo, a.sweep_hi,
+                                          a.seed_lo, a.seed_hi);
+                const int src = src_base + (t & (G - 1));
+                const uint32_t rx = __shfl_sync(FULL_MASK, batch.x, src), ry = __shfl_sync(FULL_MASK, batch.y, src);
+                const uint32_t rz = __shfl_sync(FULL_MASK, batch.z, src), rw = __shfl_sync(FULL_MASK, batch.w, src);
+                const bool act = t < n_gc;
+                const double sel = mc2d_u01(rx);
+                const int kind = !act ? 0 : (sel < a.p_ins ? 1 : (sel < a.p_ins + a.p_del ? 2 : 0));
+                const bool full = (kind == 1) && (n_own >= K);
+                const bool evaluate = (kind == 1 && !full) || (kind == 2 && n_own > 0);
+                const int i = (kind == 2 && n_own > 0) ? (int)__umulhi(ry, (uint32_t)n_own) : 0;
+                double2 pt;
+                pt.x = mc2d_u01(ry) * g.dx;
+                pt.y = mc2d_u01(rz) * g.dy;
+                if (pt.x >= g.dx) pt.x = 0.0;
+                if (pt.y >= g.dy) pt.y = 0.0;
+                const double2 old = (kind == 2 && n_own > 0) ? own[i] : make_double2(0.0, 0.0);
+                const double2 probe = (kind == 1) ? pt : old;
+                double dE = 0.0;
+                if (POT != POT_IDEAL && __any_sync(FULL_MASK, evaluate)) {
+                    double acc = 0.0;
+                    const int self = (kind == 2) ? Ms + i : -1;
+                    const int KM = min(KM0 + t, cap);  // at most t insertions so far
+                    for (int k = sl; k < KM; k += G) {
+                        const double2 c = cand[k];
+                        acc += pair_term<POT>(c.x - probe.x, c.y - probe.y, a.r2cut, a.pp, k != self);
+                    }
+                    if (cold) {
+                        for (int k = sl; k < KC; k += G) {
+                            double2 c = far2;
+                            if (evaluate && k < M - Ms)
+                                c = slow_candidate(a.pos, a.cnt, g.ghost, g.nx, g.ny, K, lcx, cy, k, x_lo, y_lo, g.Lx,
+                                                   g.Ly);
+                            acc += pair_term<POT>(c.x - probe.x, c.y - probe.y, a.r2cut, a.pp, true);
+                        }
+                    }
+                    acc = escale * group_sum<G>(acc);
+                    dE = (kind == 2) ? -acc : acc;  // MC.cpp:200,225
+                }
+                // MC.cpp:201 and :226, per-cell form
+                const double pref = (kind == 1) ? a.zA / (double)(n_own + 1) : (double)n_own / a.zA;
+                const double av = pref * exp(-a.beta * dE);
+                const bool accept = evaluate && ((av >= 1.0) || (mc2d_u01(rw) < av));
+                if (sl == 0) {
+                    if (accept && kind == 1) {
+                        own[n_own] = pt;
+                        if (a.ids) own_id[n_own] = -1;
+                    }
+                    if (accept && kind == 2) {
+                        own[i] = own[n_own - 1];
+                        own[n_own - 1] = far2;
+                        if (a.ids) own_id[i] = own_id[n_own - 1];
+                    }
+                    c_att[1] += (kind == 1);
+                    c_att[2] += (kind == 2);
+                    c_acc[1] += (accept && kind == 1);
+                    c_acc[2] += (accept && kind == 2);
+                    c_ovf += full;
+                    if (accept) dU_total += dE;
+                }
+                if (accept) n_own += (kind == 1) ? 1 : -1;
+                dirty = dirty || accept;
+                if (TRACE && sl == 0 && kind > 0) {
+                    unsigned long long slot = atomicAdd(a.trace_n, 1ull);
+                    if ((long long)slot < a.trace_cap) {
+                        mc2d_trial tr;
+                        tr.pass = a.pass; tr.cell = (int)cell_gid; tr.seq = n_disp + t; tr.kind = kind;
+                        tr.accepted = accept ? 1 : 0; tr.reserved = evaluate ? 1 : 0;
+                        const double2 o_ = (kind == 2 && evaluate) ? old : make_double2(0.0, 0.0);
+                        const double2 p_ = (kind == 1) ? pt : make_double2(0.0, 0.0);
+                        double ox_ = x_lo + o_.x, oy_ = y_lo + o_.y, nx_ = x_lo + p_.x, ny_ = y_lo + p_.y;
+                        if (ox_ >= g.Lx) ox_ -= g.Lx; if (oy_ >= g.Ly) oy_ -= g.Ly;
+                        if (nx_ >= g.Lx) nx_ -= g.Lx; if (ny_ >= g.Ly) ny_ -= g.Ly;
+                        tr.old_x = ox_; tr.old_y = oy_; tr.new_x = nx_; tr.new_y = ny_;
+                        tr.dE = evaluate ? dE : nan("");
+                        a.trace[slot] = tr;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- write the cell back (absolute coordinates) ----
+        if (dirty) {
+            for (int s = sl; s < n_own; s += G) {
+                const double2 u = own[s];
+                double x = x_lo + u.x, y = y_lo + u.y;
+                if (x >= g.Lx) x -= g.Lx; else if (x < 0.0) x += g.Lx;
+                if (y >= g.Ly) y -= g.Ly; else if (y < 0.0) y += g.Ly;
+                a.pos[(size_t)cell * K + s] = make_double2(x, y);
+                if (a.ids) a.ids[(size_t)cell * K + s] = own_id[s];
+            }
+            if (sl == 0) a.cnt[cell] = n_own;
+        }
+        // energy change of this item, summed in lane order; the slot is private to the item
+        const double dU_w = warp_sum(dU_total);
+        if (lane == 0) a.partial_dU[it0] += dU_w;
+        __syncwarp();  // the next item's staging reuses this warp's shared memory
+
+        it0 = it1;
+        it1 = it2;
+        it2 = __shfl_sync(FULL_MASK, tick, 0);
+        m0 = m1;
+        acy1 = acy2;
+    }
+
+    // ---- epilogue: move counters ----
+    unsigned int cw[7] = {c_att[0], c_att[1], c_att[2], c_acc[0], c_acc[1], c_acc[2], c_ovf};
+#pragma unroll
+    for (int q = 0; q < 7; ++q) cw[q] = (unsigned int)warp_sum_int((int)cw[q]);
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) cred[wib][q] = cw[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        unsigned long long s = 0;
+        for (int i = 0; i < wpb; ++i) s += cred[i][threadIdx.x];
+        if (s) atomicAdd(&a.counters[threadIdx.x], s);
+    }
+}
