@@ -286,11 +286,13 @@ def main():
     alg_bytes = (32.0 * st_r["attempted"][0] + 20.0 * (st_r["attempted"][1] + st_r["attempted"][2])) / nl + 8.0 * cells_per_pass
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_sweep_p<LJ, G=4> (one colour pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_sweep_p<LJ, G=%d> (one colour pass)" % info.sweep_kernel_lanes, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes, "ms_per_launch": k_ms,
                 "share_of_sweep_time": info.k_sweep_ms / max(info.last_sweep_ms, 1e-9),
                 "moves_per_s_kernel_only": sum(st_r["attempted"]) / nl / (k_ms * 1e-3),
+                "rebin_ms_per_launch": info.k_rebin_ms / max(info.k_rebin_launches, 1),
+                "halo_ms_per_sync": (info.k_halo_ms / info.k_halo_launches) if info.k_halo_launches else None,
                 "note": "path is fp64-ALU/latency bound, not HBM bound (DESIGN.md §4): low HBM fraction expected"}
     tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tr):
@@ -363,6 +365,9 @@ def main():
                        "sweeps_per_step": S, "step": "%d GCMC sweeps + 1 energy/virial reduction" % S,
                        "grid": [info.nx, info.ny], "cell_capacity": info.cell_capacity,
                        "decomposition": "1-D slabs in x, %d rank(s)" % world,
+                       "halo": {0: "none (single rank)", 1: "ncclSend/ncclRecv of whole slot columns",
+                                2: "k_halo_sync: live slots stored into the neighbours' ghost columns over NVLink "
+                                   "(CUDA IPC peer memory), flag-word sync"}[ctx.info().halo_mode],
                        "l2": "flushed between timed steps (256 MiB write on the launch stream, outside the per-step "
                              "event pairs); slot arrays are %.0f MB per buffer"
                              % (info.ncol * info.ny * info.cell_capacity * 16 / 1e6)},

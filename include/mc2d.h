@@ -215,6 +215,10 @@ typedef struct {
     long long k_sweep_launches;
     double k_rebin_ms;
     long long k_rebin_launches;
+    int halo_mode; /* 0: single rank (no halo), 1: ncclSend/ncclRecv, 2: stores into the neighbours' memory (CUDA IPC) */
+    int sweep_kernel_lanes; /* lanes per cell of the sweep kernel last launched: 4 or 8 (k_sweep_p), 32 (k_sweep) */
+    double k_halo_ms;       /* with kernel timing on: summed halo push + sync time of the last mc2d_run_sweeps */
+    long long k_halo_launches;
 } mc2d_info;
 int mc2d_get_info(mc2d_ctx *ctx, mc2d_info *out);
 /* on != 0: bracket every sweep / re-bin kernel with CUDA events (adds launch gaps: use it for the

@@ -66,7 +66,9 @@ class Info(C.Structure):
                 ("cell_dx", C.c_double), ("cell_dy", C.c_double), ("launches", C.c_longlong),
                 ("last_sweep_ms", C.c_double), ("last_energy_ms", C.c_double), ("last_pair_tests", C.c_longlong),
                 ("last_pair_evals", C.c_longlong), ("k_sweep_ms", C.c_double), ("k_sweep_launches", C.c_longlong),
-                ("k_rebin_ms", C.c_double), ("k_rebin_launches", C.c_longlong)]
+                ("k_rebin_ms", C.c_double), ("k_rebin_launches", C.c_longlong),
+                ("halo_mode", C.c_int), ("sweep_kernel_lanes", C.c_int),
+                ("k_halo_ms", C.c_double), ("k_halo_launches", C.c_longlong)]
 
 
 # every symbol include/mc2d.h declares (tests check the library exports exactly these)

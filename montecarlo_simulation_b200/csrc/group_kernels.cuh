@@ -165,3 +165,68 @@ __global__ void __launch_bounds__(256) k_rebin_g(const double2 *pos_o, const int
         if (nout > K) atomicMax(&err[0], nout);
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// K5 — halo over peer memory (replaces ParticleExchange::refreshGhosts / flushGhostUpdates,
+// particle_exchange.cpp:153-258, and the ncclSend/ncclRecv version of this library).
+//
+// A neighbour's arena is mapped into this process with CUDA IPC.  One launch per sync point:
+//   1. push: the live slots and the counts of the boundary column(s) that changed are stored
+//      directly into the neighbour's ghost column (NVLink stores, no staging buffer, no pack);
+//   2. signal: when the last CTA has finished (ticket counter + system fences) it stores the sync
+//      sequence number into the flag word of BOTH neighbours;
+//   3. wait: the same CTA spins until the neighbour(s) whose column the NEXT kernel reads have signalled
+//      the same sequence number: a pass over even columns reads only the left ghost, a pass over odd
+//      columns only the right one; re-bin, energy and download read both.
+// The kernels that follow on the stream therefore start after the ghosts they read are complete.  No
+// handshake is needed in the opposite direction: a ghost column has one writer (the neighbour, after
+// its passes of one x-parity) and one reader (this rank, in its passes of the other x-parity, which
+// wait for that writer first), the colour order is the same on every rank, and a re-bin writes the
+// other ping-pong buffer.
+// ------------------------------------------------------------------------------------------------
+struct HaloArgs {
+    const double2 *pos;  // local buffer
+    const int *cnt;
+    const int *ids;
+    double2 *dpos[2];  // [0] left neighbour's right-ghost column, [1] right neighbour's left-ghost column
+    int *dcnt[2];
+    int *dids[2];
+    unsigned long long *dflag[2];  // [0] left neighbour's "from right" word, [1] right neighbour's "from left" word
+    unsigned long long *myflag;    // [0] from left, [1] from right, [2] CTA ticket counter
+    int col[2];                    // local column pushed to the left / right neighbour
+    int push[2];
+    int wait[2];                   // wait for the left / right neighbour's signal
+    int ny, K;
+    unsigned long long seq;
+};
+
+__global__ void __launch_bounds__(256) k_halo_sync(HaloArgs h) {
+    const int per_col = h.ny * h.K;
+    const int total = (h.push[0] ? per_col : 0) + (h.push[1] ? per_col : 0);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int side = (h.push[0] && idx < per_col) ? 0 : 1;
+        const int j = idx - ((side == 1 && h.push[0]) ? per_col : 0);
+        const int cell = j / h.K, sl = j - cell * h.K;
+        const int n = h.cnt[h.col[side] * h.ny + cell];
+        if (sl < n) {
+            h.dpos[side][j] = h.pos[(size_t)h.col[side] * per_col + j];
+            if (h.ids) h.dids[side][j] = h.ids[(size_t)h.col[side] * per_col + j];
+        }
+        if (sl == 0) h.dcnt[side][cell] = n;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long ticket = atomicAdd(&h.myflag[2], 1ull);
+        if (ticket == gridDim.x - 1) {
+            __threadfence_system();
+            h.myflag[2] = 0;  // the next launch on this stream starts from zero
+            *(volatile unsigned long long *)h.dflag[0] = h.seq;
+            *(volatile unsigned long long *)h.dflag[1] = h.seq;
+            __threadfence_system();
+            const volatile unsigned long long *f = h.myflag;
+            while ((h.wait[0] && f[0] < h.seq) || (h.wait[1] && f[1] < h.seq)) __nanosleep(32);
+            __threadfence_system();
+        }
+    }
+}

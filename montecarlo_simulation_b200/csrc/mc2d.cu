@@ -63,6 +63,7 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) =
         nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool load(std::string &err) {
         if (handle) return true;
@@ -81,7 +82,7 @@ struct NcclApi {
         return false;                                                         \
     }
         MC2D_SYM(GetUniqueId) MC2D_SYM(CommInitRank) MC2D_SYM(CommDestroy) MC2D_SYM(Send) MC2D_SYM(Recv)
-        MC2D_SYM(GroupStart) MC2D_SYM(GroupEnd) MC2D_SYM(AllReduce) MC2D_SYM(GetErrorString)
+        MC2D_SYM(GroupStart) MC2D_SYM(GroupEnd) MC2D_SYM(AllReduce) MC2D_SYM(AllGather) MC2D_SYM(GetErrorString)
 #undef MC2D_SYM
         return true;
     }
@@ -112,6 +113,15 @@ struct mc2d_ctx {
     int *cnt[2] = {nullptr, nullptr};
     int *ids[2] = {nullptr, nullptr};
     int allocK = 0;
+    // One arena holds the sync flags and both slot buffers: a neighbour rank maps it with ONE CUDA IPC
+    // handle and writes its boundary column straight into this rank's ghost column over NVLink.
+    char *arena = nullptr;
+    size_t off_pos[2] = {0, 0}, off_cnt[2] = {0, 0}, off_ids[2] = {0, 0};
+    char *peer_base[2] = {nullptr, nullptr};  // [0] left, [1] right neighbour's arena (the same mapping when nranks == 2)
+    bool peers_valid = false;                 // peer_base matches the neighbours' current arenas
+    bool p2p = false;                         // halo over peer memory (k_halo_sync); false: ncclSend/ncclRecv
+    unsigned long long halo_seq = 0;          // sync points so far; every rank counts the same ones
+    int last_G = 0;                           // lanes per cell of the last sweep launch (0: k_sweep)
 
     unsigned long long *d_counters = nullptr;  // 8
     double *d_energy = nullptr;                // [0] running, [1] U, [2] W, [3] N
@@ -135,8 +145,8 @@ struct mc2d_ctx {
     bool ktiming = false;
     std::vector<cudaEvent_t> kev;  // event pool for per-kernel timing
     std::vector<int> kev_kind;     // 0 sweep, 1 rebin (one entry per event PAIR used in this call)
-    double k_sweep_ms = 0, k_rebin_ms = 0;
-    long long k_sweep_launches = 0, k_rebin_launches = 0;
+    double k_sweep_ms = 0, k_rebin_ms = 0, k_halo_ms = 0;
+    long long k_sweep_launches = 0, k_rebin_launches = 0, k_halo_launches = 0;
 
 #if MC2D_HAVE_NCCL_H
     ncclComm_t comm = nullptr;
@@ -320,11 +330,19 @@ extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
     return MC2D_OK;
 }
 
+static void close_peers(mc2d_ctx *ctx) {
+    if (ctx->peer_base[0]) cudaIpcCloseMemHandle(ctx->peer_base[0]);
+    if (ctx->peer_base[1] && ctx->peer_base[1] != ctx->peer_base[0]) cudaIpcCloseMemHandle(ctx->peer_base[1]);
+    ctx->peer_base[0] = ctx->peer_base[1] = nullptr;
+    ctx->peers_valid = false;
+    ctx->p2p = false;
+}
+
 static void free_slots(mc2d_ctx *ctx) {
+    close_peers(ctx);
+    if (ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = nullptr;
     for (int b = 0; b < 2; ++b) {
-        if (ctx->pos[b]) cudaFree(ctx->pos[b]);
-        if (ctx->cnt[b]) cudaFree(ctx->cnt[b]);
-        if (ctx->ids[b]) cudaFree(ctx->ids[b]);
         ctx->pos[b] = nullptr;
         ctx->cnt[b] = nullptr;
         ctx->ids[b] = nullptr;
@@ -422,23 +440,127 @@ static int h2d_positions(mc2d_ctx *ctx, const double *xy, long long n) {
 // ------------------------------------------------------------------------------------------------
 // halo exchange (K5): a cell column is contiguous, so no pack kernel is needed
 // ------------------------------------------------------------------------------------------------
-static int halo_exchange(mc2d_ctx *ctx, int buf, bool left, bool right) {
+#if MC2D_HAVE_NCCL_H
+#define NC(call)                                                                                  \
+    do {                                                                                          \
+        ncclResult_t r__ = (call);                                                                \
+        if (r__ != ncclSuccess) FAIL(MC2D_ERR_NCCL, "%s: %s", #call, g_nccl.GetErrorString(r__)); \
+    } while (0)
+#endif
+
+// all ranks meet (and the stream drains)
+static int comm_barrier(mc2d_ctx *ctx) {
+#if MC2D_HAVE_NCCL_H
+    CU(ctx->outI.ensure(256));
+    NC(g_nccl.AllReduce(ctx->outI.p, ctx->outI.p, 1, ncclInt, ncclSum, ctx->comm, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+#endif
+    return MC2D_OK;
+}
+
+// element-wise MAX of one int over the ranks (agrees on the cell capacity)
+static int comm_max_int(mc2d_ctx *ctx, int *v) {
+#if MC2D_HAVE_NCCL_H
+    CU(ctx->outI.ensure(256));
+    CU(cudaMemcpyAsync(ctx->outI.p, v, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    NC(g_nccl.AllReduce(ctx->outI.p, ctx->outI.p, 1, ncclInt, ncclMax, ctx->comm, ctx->stream));
+    CU(cudaMemcpyAsync(v, ctx->outI.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+#endif
+    return MC2D_OK;
+}
+
+// Maps the arenas of the left and right neighbour (CUDA IPC; the 64-byte handles travel by ncclAllGather).
+// Collective.  If any rank cannot map a neighbour, every rank falls back to ncclSend/ncclRecv.
+static int connect_peers(mc2d_ctx *ctx) {
+#if MC2D_HAVE_NCCL_H
+    const int R = ctx->prm.nranks, me = ctx->prm.rank;
+    close_peers(ctx);
+    int ok = 1;
+    if (const char *e = getenv("MC2D_HALO"))
+        if (!strcmp(e, "nccl")) ok = 0;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (ok && cudaIpcGetMemHandle(&mine, ctx->arena) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+    }
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    CU(ctx->outC.ensure(hb * (size_t)(R + 1)));
+    char *dsend = ctx->outC.as<char>(), *drecv = dsend + hb;
+    CU(cudaMemcpyAsync(dsend, &mine, hb, cudaMemcpyHostToDevice, ctx->stream));
+    NC(g_nccl.AllGather(dsend, drecv, hb, ncclChar, ctx->comm, ctx->stream));
+    std::vector<cudaIpcMemHandle_t> all((size_t)R);
+    CU(cudaMemcpyAsync(all.data(), drecv, hb * (size_t)R, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const int nb[2] = {(me + R - 1) % R, (me + 1) % R};
+    for (int side = 0; side < 2 && ok; ++side) {
+        if (side == 1 && nb[1] == nb[0]) {
+            ctx->peer_base[1] = ctx->peer_base[0];
+            break;
+        }
+        void *ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[(size_t)nb[side]], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+        } else {
+            ctx->peer_base[side] = static_cast<char *>(ptr);
+        }
+    }
+    int all_ok = ok ? 0 : 1;  // max over ranks of "failed"
+    if (int rc = comm_max_int(ctx, &all_ok)) return rc;
+    if (all_ok != 0) close_peers(ctx);
+    ctx->p2p = (all_ok == 0);
+    ctx->peers_valid = true;
+#endif
+    return MC2D_OK;
+}
+
+static int halo_exchange(mc2d_ctx *ctx, int buf, bool left, bool right, bool wait_left = true, bool wait_right = true) {
 #if MC2D_HAVE_NCCL_H
     const Grid &g = ctx->g;
     if (!g.ghost) return MC2D_OK;
     if (!ctx->have_comm) FAIL(MC2D_ERR_STATE, "nranks > 1 but mc2d_comm_init was not called");
+    if (!ctx->peers_valid)
+        if (int rc = connect_peers(ctx)) return rc;
+    const int first = g.ghost, last = g.ghost + g.ncol - 1, lghost = 0, rghost = g.ghost + g.ncol;
+    if (ctx->p2p) {
+        const size_t colp = (size_t)g.ny * g.K, colc = (size_t)g.ny;
+        HaloArgs h;
+        h.pos = ctx->pos[buf];
+        h.cnt = ctx->cnt[buf];
+        h.ids = ctx->use_ids ? ctx->ids[buf] : nullptr;
+        const int ghost_col[2] = {rghost, lghost};  // my first column lands in the LEFT neighbour's RIGHT ghost
+        for (int side = 0; side < 2; ++side) {
+            char *pb = ctx->peer_base[side];
+            h.dpos[side] = reinterpret_cast<double2 *>(pb + ctx->off_pos[buf]) + (size_t)ghost_col[side] * colp;
+            h.dcnt[side] = reinterpret_cast<int *>(pb + ctx->off_cnt[buf]) + (size_t)ghost_col[side] * colc;
+            h.dids[side] = ctx->use_ids ? reinterpret_cast<int *>(pb + ctx->off_ids[buf]) + (size_t)ghost_col[side] * colp
+                                        : nullptr;
+            h.dflag[side] = reinterpret_cast<unsigned long long *>(pb) + (side == 0 ? 1 : 0);
+        }
+        h.myflag = reinterpret_cast<unsigned long long *>(ctx->arena);
+        h.col[0] = first;
+        h.col[1] = last;
+        h.push[0] = left ? 1 : 0;
+        h.push[1] = right ? 1 : 0;
+        h.wait[0] = wait_left ? 1 : 0;
+        h.wait[1] = wait_right ? 1 : 0;
+        h.ny = g.ny;
+        h.K = g.K;
+        h.seq = ++ctx->halo_seq;
+        const int total = (int)colp * (h.push[0] + h.push[1]);
+        const int nblk = std::max(1, std::min(4 * ctx->num_sms, (total + 255) / 256));
+        k_halo_sync<<<nblk, 256, 0, ctx->stream>>>(h);
+        ctx->launches++;
+        return MC2D_OK;
+    }
     const int R = ctx->prm.nranks, me = ctx->prm.rank;
     const int lrank = (me + R - 1) % R, rrank = (me + 1) % R;
     const size_t colp = (size_t)g.ny * g.K, colc = (size_t)g.ny;
     auto col_pos = [&](int c) { return ctx->pos[buf] + (size_t)c * colp; };
     auto col_cnt = [&](int c) { return ctx->cnt[buf] + (size_t)c * colc; };
     auto col_ids = [&](int c) { return ctx->ids[buf] + (size_t)c * colp; };
-    const int first = g.ghost, last = g.ghost + g.ncol - 1, lghost = 0, rghost = g.ghost + g.ncol;
-#define NC(call)                                                                                  \
-    do {                                                                                          \
-        ncclResult_t r__ = (call);                                                                \
-        if (r__ != ncclSuccess) FAIL(MC2D_ERR_NCCL, "%s: %s", #call, g_nccl.GetErrorString(r__)); \
-    } while (0)
     NC(g_nccl.GroupStart());
     if (left) {  // my first owned column -> left neighbour's right ghost; my right ghost <- right neighbour
         NC(g_nccl.Send(col_pos(first), colp * sizeof(double2), ncclChar, lrank, ctx->comm, ctx->stream));
@@ -468,15 +590,40 @@ static int halo_exchange(mc2d_ctx *ctx, int buf, bool left, bool right) {
 // ------------------------------------------------------------------------------------------------
 // slot storage
 // ------------------------------------------------------------------------------------------------
+static int comm_barrier(mc2d_ctx *ctx);
+
 static int alloc_slots(mc2d_ctx *ctx, int K) {
+    // Neighbours may have this arena mapped and this rank theirs: every rank closes its mappings, then all
+    // meet, then each frees.  (mc2d_upload is collective when nranks > 1.)
+    close_peers(ctx);
+    if (ctx->arena && ctx->have_comm && ctx->prm.nranks > 1)
+        if (int rc = comm_barrier(ctx)) return rc;
     free_slots(ctx);
     const size_t ncell = (size_t)ctx->g.ncs * ctx->g.ny;
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    size_t off = 256;  // [0] flag from left, [1] flag from right, [2] CTA ticket of k_halo_sync
     for (int b = 0; b < 2; ++b) {
-        CU(cudaMalloc(&ctx->pos[b], sizeof(double2) * ncell * K));
-        CU(cudaMalloc(&ctx->cnt[b], sizeof(int) * ncell));
-        CU(cudaMemsetAsync(ctx->cnt[b], 0, sizeof(int) * ncell, ctx->stream));
-        if (ctx->use_ids) CU(cudaMalloc(&ctx->ids[b], sizeof(int) * ncell * K));
+        ctx->off_pos[b] = off;
+        off += up(sizeof(double2) * ncell * K);
     }
+    for (int b = 0; b < 2; ++b) {
+        ctx->off_cnt[b] = off;
+        off += up(sizeof(int) * ncell);
+    }
+    for (int b = 0; b < 2; ++b) {
+        ctx->off_ids[b] = off;
+        if (ctx->use_ids) off += up(sizeof(int) * ncell * K);
+    }
+    CU(cudaMalloc(&ctx->arena, off));
+    CU(cudaMemsetAsync(ctx->arena, 0, 256, ctx->stream));
+    ctx->halo_seq = 0;
+    for (int b = 0; b < 2; ++b) {
+        ctx->pos[b] = reinterpret_cast<double2 *>(ctx->arena + ctx->off_pos[b]);
+        ctx->cnt[b] = reinterpret_cast<int *>(ctx->arena + ctx->off_cnt[b]);
+        ctx->ids[b] = ctx->use_ids ? reinterpret_cast<int *>(ctx->arena + ctx->off_ids[b]) : nullptr;
+        CU(cudaMemsetAsync(ctx->cnt[b], 0, sizeof(int) * ncell, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
     ctx->allocK = K;
     ctx->g.K = K;
     return MC2D_OK;
@@ -526,6 +673,8 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
     int maxcount = 0;
     CU(cudaMemcpyAsync(&maxcount, ctx->d_err + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (g.ghost && ctx->have_comm)  // every slab must use the same capacity: the halo copies whole slot columns
+        if ((rc = comm_max_int(ctx, &maxcount))) return rc;
     int K = auto_capacity(ctx, maxcount);
     if (K > 1024) FAIL(MC2D_ERR_CELL_OVERFLOW, "a cell holds %d particles; capacity %d exceeds the 1024-slot limit", maxcount, K);
     if (K != ctx->allocK || (ctx->use_ids && !ctx->ids[0])) {
@@ -998,6 +1147,7 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
     }
     const bool persistent = G != 0;
+    ctx->last_G = G;
     const int cells_per_block = G ? wpb * (32 / G) : wpb;
     // k_sweep_p: a work item = 32/G cells of one column pair; k_sweep: one CTA per cells_per_block
     const int nitems = G ? (g.ncol / 2) * ((g.ny / 2 + 32 / G - 1) / (32 / G)) : 0;
@@ -1042,8 +1192,13 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             ctx->cur = nb;
             g = gn;
             ctx->order_valid = false;
-            int rc = halo_exchange(ctx, ctx->cur, true, true);
+            const bool even_next = (order[0] & 1) == 0;  // the first pass reads the left ghost (even columns) or the right one
+            if (g.ghost)
+                if (int rc = ktime_begin(ctx, 2)) return rc;
+            int rc = halo_exchange(ctx, ctx->cur, true, true, even_next, !even_next);
             if (rc) return rc;
+            if (g.ghost)
+                if ((rc = ktime_end(ctx))) return rc;
         }
         if (persistent) {
             if (!ctx->order_valid)
@@ -1106,8 +1261,12 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             if ((rc = ktime_end(ctx))) return rc;
             if (g.ghost) {
                 const bool left = (order[p] & 1) == 0;
-                rc = halo_exchange(ctx, ctx->cur, left, !left);
+                // what the next kernel on the stream reads: one ghost for a pass, both for re-bin / energy / download
+                const bool even_next = p < 3 && (order[p + 1] & 1) == 0;
+                if ((rc = ktime_begin(ctx, 2))) return rc;
+                rc = halo_exchange(ctx, ctx->cur, left, !left, p == 3 || even_next, p == 3 || !even_next);
                 if (rc) return rc;
+                if ((rc = ktime_end(ctx))) return rc;
             }
         }
         ctx->sweep++;
@@ -1125,17 +1284,20 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_sweep_ms = ms;
     if (ctx->ktiming) {
-        ctx->k_sweep_ms = ctx->k_rebin_ms = 0;
-        ctx->k_sweep_launches = ctx->k_rebin_launches = 0;
+        ctx->k_sweep_ms = ctx->k_rebin_ms = ctx->k_halo_ms = 0;
+        ctx->k_sweep_launches = ctx->k_rebin_launches = ctx->k_halo_launches = 0;
         for (size_t i = 0; i < ctx->kev_kind.size(); ++i) {
             float t = 0;
             CU(cudaEventElapsedTime(&t, ctx->kev[2 * i], ctx->kev[2 * i + 1]));
             if (ctx->kev_kind[i] == 0) {
                 ctx->k_sweep_ms += t;
                 ctx->k_sweep_launches++;
-            } else {
+            } else if (ctx->kev_kind[i] == 1) {
                 ctx->k_rebin_ms += t;
                 ctx->k_rebin_launches++;
+            } else {
+                ctx->k_halo_ms += t;
+                ctx->k_halo_launches++;
             }
         }
     }
@@ -1317,6 +1479,10 @@ extern "C" int mc2d_get_info(mc2d_ctx *ctx, mc2d_info *o) {
     o->k_sweep_launches = ctx->k_sweep_launches;
     o->k_rebin_ms = ctx->k_rebin_ms;
     o->k_rebin_launches = ctx->k_rebin_launches;
+    o->halo_mode = !ctx->g.ghost ? 0 : (ctx->p2p ? 2 : 1);
+    o->k_halo_ms = ctx->k_halo_ms;
+    o->k_halo_launches = ctx->k_halo_launches;
+    o->sweep_kernel_lanes = ctx->last_G ? ctx->last_G : 32;
     return MC2D_OK;
 }
 
