@@ -230,3 +230,127 @@ __global__ void __launch_bounds__(256) k_halo_sync(HaloArgs h) {
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// K4 on the slot layout, production variant (computeTotalEnergyCellList + computeTotalVirialCellList,
+// thermodynamic_calculator.cpp:194-242; ThermodynamicCalculatorParallel::totalEnergy/totalVirial,
+// thermodynamic_calculator_parallel.cpp:56-145): one pass for U and W.
+//
+// Same decomposition as k_sweep_p: G lanes per cell, 32/G cells per warp, the work items of
+// k_order_local (equally full cells share a warp), candidates staged by cp.async into shared memory
+// as cell-local coordinates.  Half shell: a cell pairs its own particles (j > i) and those of its 4
+// forward neighbours (0,+1), (+1,-1), (+1,0), (+1,+1), so every unordered pair is evaluated once; in a
+// slab the last owned column pairs with the right ghost column and the first one leaves its left
+// pairs to the left rank.  LJ / WCA accumulate a = sum r^-12 and b = sum r^-6 (one reciprocal with one
+// Newton step per pair): U = 4 (a - b) [+ 1 per WCA pair], W = 48 a - 24 b.
+// Items whose candidates do not fit in the group's shared memory raise err[3]; the host then repeats
+// the reduction with k_energy_virial_g.
+// ------------------------------------------------------------------------------------------------
+template <int POT, int G>
+__global__ void __launch_bounds__(256) k_energy_p(const double2 *pos, const int *cnt, const int *perm, Grid g,
+                                                  PairParams pp, double r2cut, int nitems, int cap, int stride,
+                                                  double *partU, double *partW, unsigned long long *pair_stats,
+                                                  int *err) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    constexpr int GPW = 32 / G;
+    const int K = g.K;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int gi = lane / G, sl = lane % G;
+    double2 *cand = reinterpret_cast<double2 *>(smem_raw + (size_t)(wib * GPW + gi) * stride);
+    const int nay = g.ny >> 1, npairs = g.ncol >> 1;
+    const int idx = blockIdx.x * wpb + wib;  // heavy-first over (item, colour)
+    const int colour = idx & 3, item = idx >> 2;
+    const int px = colour & 1, py = colour >> 1;
+    const double hLx = 0.5 * g.Lx, hLy = 0.5 * g.Ly;
+
+    int acy = -1;
+    const int p = item % npairs, j = (item / npairs) * GPW + gi;
+    if (item < nitems && j < nay) acy = perm[((size_t)colour * npairs + p) * nay + j];
+    const int lcx = g.ghost + 2 * p + px, cy = 2 * max(acy, 0) + py, gcx = g.col0 + 2 * p + px;
+    int col3[3], row3[3];
+    nbr_rows_cols(g, lcx, cy, col3, row3);
+    int n_own = 0, nf[4] = {0, 0, 0, 0}, cf[4];
+    cf[0] = col3[1] + row3[2];  // ( 0, +1)
+    cf[1] = col3[2] + row3[0];  // (+1, -1)
+    cf[2] = col3[2] + row3[1];  // (+1,  0)
+    cf[3] = col3[2] + row3[2];  // (+1, +1)
+    if (acy >= 0) {
+        n_own = cnt[col3[1] + row3[1]];
+        if (n_own > 0 && POT != POT_IDEAL) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) nf[q] = cnt[cf[q]];
+        }
+    }
+    int Mf = nf[0] + nf[1] + nf[2] + nf[3];
+    if (Mf + n_own > cap) {  // does not fit: the host falls back to the unstaged kernel
+        if (sl == 0) atomicExch(&err[3], 1);
+        Mf = 0;
+        n_own = 0;
+    }
+    const bool work = n_own > 0 && POT != POT_IDEAL;
+    const double x_lo = g.ox + gcx * g.dx, y_lo = g.oy + cy * g.dy;
+    if (work) {
+        for (int s = sl; s < n_own; s += G) cp_async16(&cand[Mf + s], &pos[(size_t)(col3[1] + row3[1]) * K + s]);
+        int pre = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if ((q % G) == sl)
+                for (int s = 0; s < nf[q]; ++s) cp_async16(&cand[pre + s], &pos[(size_t)cf[q] * K + s]);
+            pre += nf[q];
+        }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    const int ntot = work ? Mf + n_own : 0;
+    const int KM = warp_max_int(ntot), N0 = warp_max_int(work ? n_own : 0);
+    const double2 far2 = make_double2(MC2D_FAR, MC2D_FAR);
+    for (int k = sl; k < ntot; k += G) cand[k] = to_local(cand[k], x_lo, y_lo, g, hLx, hLy);
+    for (int k = ntot + sl; k < min(KM, cap); k += G) cand[k] = far2;
+    __syncwarp();
+
+    double a = 0.0, b = 0.0, accU = 0.0, accW = 0.0;
+    unsigned int evals = 0;
+    for (int i = 0; i < N0; ++i) {
+        // an idle group probes from the opposite far corner: every distance is ~2e150, beyond the cutoff
+        const double2 ui = (i < n_own) ? cand[Mf + i] : make_double2(-MC2D_FAR, -MC2D_FAR);
+        const int first_own = Mf + i;  // own candidates count from j > i
+        for (int k = sl; k < KM; k += G) {
+            const double2 c = cand[k];
+            const double dx = c.x - ui.x, dy = c.y - ui.y;
+            const double r2 = fma(dx, dx, dy * dy);
+            bool ok = (k < Mf || k > first_own) && r2 <= r2cut;  // inclusive cutoff, cell_list.cpp:62
+            if (POT == POT_LJ || POT == POT_WCA) {
+                if (POT == POT_WCA) ok = ok && r2 < 1.2599;
+                const double r2m = __hiloint2double(ok ? __double2hiint(r2) : 0x7E37E43C, __double2loint(r2));
+                const double ri = rcp_newton1(r2m);
+                const double r6 = ri * ri * ri;
+                a = fma(r6, r6, a);
+                b += r6;
+            } else if (ok) {
+                double u, w;
+                pair_uw<POT>(r2, pp, u, w);
+                accU += u;
+                accW += w;
+            }
+            evals += ok;
+        }
+    }
+    if (POT == POT_LJ || POT == POT_WCA) {
+        accU = 4.0 * (a - b) + (POT == POT_WCA ? (double)evals : 0.0);
+        accW = 48.0 * a - 24.0 * b;
+    }
+    const double sU = block_sum(accU, red);
+    const double sW = block_sum(accW, red);
+    if (threadIdx.x == 0) {
+        partU[blockIdx.x] = sU;
+        partW[blockIdx.x] = sW;
+    }
+    // distance tests of this cell: n * Mf forward pairs + n (n - 1) / 2 own pairs
+    const unsigned int tests_g = (sl == 0 && work) ? (unsigned int)(n_own * Mf + n_own * (n_own - 1) / 2) : 0u;
+    const unsigned int t = (unsigned int)warp_sum_int((int)tests_g), e = (unsigned int)warp_sum_int((int)evals);
+    if (lane == 0 && pair_stats && (t | e)) {
+        atomicAdd(&pair_stats[0], (unsigned long long)t);
+        atomicAdd(&pair_stats[1], (unsigned long long)e);
+    }
+}

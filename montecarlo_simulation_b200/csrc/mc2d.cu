@@ -764,6 +764,146 @@ extern "C" int mc2d_download(mc2d_ctx *ctx, double *xy, int *ids, long long cap,
     return MC2D_OK;
 }
 
+// Launch shape of the kernels that work on sorted items (k_sweep_p, k_energy_p): lanes per cell, neighbour
+// slots and bytes per group, warps per CTA.  G = 0: the grid or the cells do not fit that layout.
+struct ItemLayout {
+    int G = 0, nb_cap = 0, wpb = 8;
+    size_t per_group = 0;
+};
+
+static int item_layout(mc2d_ctx *ctx, ItemLayout *out) {
+    const Grid &g = ctx->g;
+    const int K = g.K;
+    const bool ideal = ctx->prm.potential == MC2D_IDEAL;
+    const bool minimg = (g.nx < 4 || g.ny < 4);
+    int wpb = 8;
+    // Kernel choice: k_sweep_p (G lanes per cell, persistent warps over the sorted work list) unless the
+    // grid needs the per-pair minimum image or the cells are too big for its shared-memory layout; then
+    // k_sweep (one warp per cell).  G follows the expected number of candidates per cell (9 cells x mean
+    // occupancy): measured on config #4 (28 candidates), G = 4 beats 8 and 2; denser neighbourhoods
+    // (> 64 candidates) fill 8 lanes.  MC2D_SWEEP_G overrides (0 = k_sweep), for tuning and tests.
+    int G = 0, nb_cap = 0;
+    size_t per_group = 0;  // bytes between the candidate arrays of two groups
+    if (!minimg && K <= 255) {
+        const double n_c = (double)std::max<long long>(ctx->n_last, 1) / std::max(1, g.ncol * g.ny);
+        G = (9.0 * n_c > 64.0) ? 8 : 4;
+        if (const char *e = getenv("MC2D_SWEEP_G")) G = atoi(e);
+        if (G != 0 && G != 4 && G != 8) FAIL(MC2D_ERR_INVALID, "MC2D_SWEEP_G must be 0, 4 or 8");
+        if (G) {
+            // A quarter warp (8 lanes x 16 B) must touch 32 distinct banks: the groups inside it sit
+            // G*16 bytes apart modulo 128 (profiles/r01f: an unpadded stride doubled every LDS.128).
+            const size_t resid = (size_t)(G * 16) % 128;
+            auto stride_of = [&](int nb) {
+                const size_t b = (size_t)(nb + K) * sizeof(double2) + (ctx->use_ids ? (size_t)K * sizeof(int) : 0);
+                size_t st = b / 128 * 128 + resid;
+                return st < b ? st + 128 : st;
+            };
+            const int nb_want = ideal ? 0 : std::min(8 * K, even_up((int)(8.0 * n_c * 1.6 + 12.0), 4));
+            const int nb_min = ideal ? 0 : std::min(8 * K, even_up((int)(8.0 * n_c * 1.25 + 8.0), 4));
+            // largest neighbour capacity that leaves 24 warps per SM (9 KB of shared memory per warp)
+            int w0 = 8;
+            if (const char *e = getenv("MC2D_SWEEP_WPB")) w0 = std::max(1, std::min(8, atoi(e)));  // tuning
+            const size_t warp_budget = 72 * 1024 / 8;
+            bool found = false;
+            for (int nb = nb_want; nb >= nb_min && !found; nb -= 4)
+                if (stride_of(nb) * (32 / G) <= warp_budget) {
+                    wpb = w0;
+                    nb_cap = nb;
+                    found = true;
+                }
+            if (!found) {  // big cells: fewer warps per SM, then one warp per cell
+                nb_cap = nb_want;
+                wpb = w0;
+                while (wpb > 1 && stride_of(nb_cap) * (32 / G) * wpb > 200 * 1024) wpb >>= 1;
+                if (stride_of(nb_cap) * (32 / G) * wpb > 200 * 1024) G = 0;
+            }
+            per_group = stride_of(nb_cap);
+        }
+    }
+    out->G = G;
+    out->nb_cap = nb_cap;
+    out->wpb = wpb;
+    out->per_group = per_group;
+    return MC2D_OK;
+}
+
+// per colour and column pair: active cells by falling (occupancy, candidates) -> ctx->order_buf
+static int build_order(mc2d_ctx *ctx) {
+    const Grid &g = ctx->g;
+    const int ncell = g.ncol * g.ny;
+    const size_t smem = sizeof(int) * (size_t)(3 * g.ny + g.ny / 2);
+    if (smem > 200 * 1024) FAIL(MC2D_ERR_GEOMETRY, "grid has %d rows: too many for k_order_local", g.ny);
+    static bool attr = false;
+    if (smem > 40 * 1024 && !attr) {
+        CU(cudaFuncSetAttribute(k_order_local, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    CU(ctx->order_buf.ensure(sizeof(int) * (size_t)ncell));
+    k_order_local<<<dim3(g.ncol / 2, 4), 256, smem, ctx->stream>>>(g, ctx->cnt[ctx->cur], ctx->order_buf.as<int>());
+    ctx->launches++;
+    ctx->order_valid = true;
+    return MC2D_OK;
+}
+
+
+// K4 on the slot layout through the sorted items (k_energy_p).  *done = false: not applicable here (tiny grid,
+// huge cells) or an item did not fit its shared memory — the caller uses k_energy_virial_g instead.
+static int launch_energy_items(mc2d_ctx *ctx, double *U, double *W, bool *done) {
+    *done = false;
+    const Grid &g = ctx->g;
+    if (g.nx < 4 || g.ny < 4) return MC2D_OK;
+    ItemLayout lay;
+    if (int rc = item_layout(ctx, &lay)) return rc;
+    if (!lay.G) return MC2D_OK;
+    if (!ctx->order_valid)  // any permutation of the cells is correct; a fresh one balances the warps
+        if (int rc = build_order(ctx)) return rc;
+    const int G = lay.G, wpb = lay.wpb;
+    const int nitems = (g.ncol / 2) * ((g.ny / 2 + 32 / G - 1) / (32 / G));
+    const int nblocks = (4 * nitems + wpb - 1) / wpb;
+    const size_t smem = lay.per_group * (32 / G) * wpb;
+    const int cap = lay.nb_cap + g.K;
+    CU(ctx->partial.ensure(sizeof(double) * 2 * (size_t)nblocks));
+    double *pU = ctx->partial.as<double>(), *pW = pU + nblocks;
+    CU(cudaMemsetAsync(ctx->d_pair_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_err + 3, 0, sizeof(int), ctx->stream));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    DISPATCH_POT(ctx->prm.potential, {
+        if (G == 4) {
+            CU(cudaFuncSetAttribute(k_energy_p<POT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            k_energy_p<POT, 4><<<nblocks, wpb * 32, smem, ctx->stream>>>(
+                ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->order_buf.as<int>(), g, ctx->pp, ctx->r2cut, nitems, cap,
+                (int)lay.per_group, pU, pW, ctx->d_pair_stats, ctx->d_err);
+        } else {
+            CU(cudaFuncSetAttribute(k_energy_p<POT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            k_energy_p<POT, 8><<<nblocks, wpb * 32, smem, ctx->stream>>>(
+                ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->order_buf.as<int>(), g, ctx->pp, ctx->r2cut, nitems, cap,
+                (int)lay.per_group, pU, pW, ctx->d_pair_stats, ctx->d_err);
+        }
+    });
+    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(pU, nblocks, 1.0, ctx->d_energy + 1, 0);
+    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(pW, nblocks, 1.0, ctx->d_energy + 2, 0);
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->launches += 3;
+    double uw[2];
+    unsigned long long ps[2];
+    int ovf = 0;
+    CU(cudaMemcpyAsync(uw, ctx->d_energy + 1, sizeof uw, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ps, ctx->d_pair_stats, sizeof ps, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&ovf, ctx->d_err + 3, sizeof ovf, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    if (ovf) return MC2D_OK;
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_energy_ms = ms;
+    ctx->last_tests = (long long)ps[0];
+    ctx->last_evals = (long long)ps[1];
+    *U = uw[0];
+    *W = uw[1];
+    *done = true;
+    return MC2D_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K4 launches
 // ------------------------------------------------------------------------------------------------
@@ -811,7 +951,11 @@ static int energy_on_slots(mc2d_ctx *ctx, double *U, double *W, long long *N, bo
     const Grid &g = ctx->g;
     SlotView v{ctx->pos[ctx->cur], ctx->cnt[ctx->cur], g};
     const int half = (g.nx >= 3 && g.ny >= 3) ? 1 : 0;
-    int rc = launch_energy(ctx, v, g.ncol * g.ny, half, false, nullptr, nullptr, U, W);
+    bool done = false;
+    int rc = MC2D_OK;
+    if (!getenv("MC2D_ENERGY_UNSTAGED")) rc = launch_energy_items(ctx, U, W, &done);
+    if (rc) return rc;
+    if (!done) rc = launch_energy(ctx, v, g.ncol * g.ny, half, false, nullptr, nullptr, U, W);
     if (rc) return rc;
     long long n = 0;
     rc = count_particles(ctx, &n);
@@ -1045,24 +1189,6 @@ static int ktime_end(mc2d_ctx *ctx) {
     return MC2D_OK;
 }
 
-// per colour and column pair: active cells by falling (occupancy, candidates) -> ctx->order_buf
-static int build_order(mc2d_ctx *ctx) {
-    const Grid &g = ctx->g;
-    const int ncell = g.ncol * g.ny;
-    const size_t smem = sizeof(int) * (size_t)(3 * g.ny + g.ny / 2);
-    if (smem > 200 * 1024) FAIL(MC2D_ERR_GEOMETRY, "grid has %d rows: too many for k_order_local", g.ny);
-    static bool attr = false;
-    if (smem > 40 * 1024 && !attr) {
-        CU(cudaFuncSetAttribute(k_order_local, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
-    }
-    CU(ctx->order_buf.ensure(sizeof(int) * (size_t)ncell));
-    k_order_local<<<dim3(g.ncol / 2, 4), 256, smem, ctx->stream>>>(g, ctx->cnt[ctx->cur], ctx->order_buf.as<int>());
-    ctx->launches++;
-    ctx->order_valid = true;
-    return MC2D_OK;
-}
-
 template <int POT, int G, bool TRACE>
 static int launch_sweep_p(mc2d_ctx *ctx, const SweepArgs &a, int wpb, size_t smem, int nb_cap, int stride) {
     static size_t smem_seen = (size_t)-1;  // per instantiation: resident CTAs per SM for this launch shape
@@ -1099,49 +1225,11 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
     if (per_warp * wpb > 200 * 1024) FAIL(MC2D_ERR_CELL_OVERFLOW, "cell capacity %d needs too much shared memory", K);
     const int nact = (g.ncol / 2) * (g.ny / 2);
-    // Kernel choice: k_sweep_p (G lanes per cell, persistent warps over the sorted work list) unless the
-    // grid needs the per-pair minimum image or the cells are too big for its shared-memory layout; then
-    // k_sweep (one warp per cell).  G follows the expected number of candidates per cell (9 cells x mean
-    // occupancy): measured on config #4 (28 candidates), G = 4 beats 8 and 2; denser neighbourhoods
-    // (> 64 candidates) fill 8 lanes.  MC2D_SWEEP_G overrides (0 = k_sweep), for tuning and tests.
-    int G = 0, nb_cap = 0;
-    size_t per_group = 0;  // bytes between the candidate arrays of two groups
-    if (!minimg && K <= 255) {
-        const double n_c = (double)std::max<long long>(ctx->n_last, 1) / std::max(1, g.ncol * g.ny);
-        G = (9.0 * n_c > 64.0) ? 8 : 4;
-        if (const char *e = getenv("MC2D_SWEEP_G")) G = atoi(e);
-        if (G != 0 && G != 4 && G != 8) FAIL(MC2D_ERR_INVALID, "MC2D_SWEEP_G must be 0, 4 or 8");
-        if (G) {
-            // A quarter warp (8 lanes x 16 B) must touch 32 distinct banks: the groups inside it sit
-            // G*16 bytes apart modulo 128 (profiles/r01f: an unpadded stride doubled every LDS.128).
-            const size_t resid = (size_t)(G * 16) % 128;
-            auto stride_of = [&](int nb) {
-                const size_t b = (size_t)(nb + K) * sizeof(double2) + (ctx->use_ids ? (size_t)K * sizeof(int) : 0);
-                size_t st = b / 128 * 128 + resid;
-                return st < b ? st + 128 : st;
-            };
-            const int nb_want = ideal ? 0 : std::min(8 * K, even_up((int)(8.0 * n_c * 1.6 + 12.0), 4));
-            const int nb_min = ideal ? 0 : std::min(8 * K, even_up((int)(8.0 * n_c * 1.25 + 8.0), 4));
-            // largest neighbour capacity that leaves 24 warps per SM (9 KB of shared memory per warp)
-            int w0 = 8;
-            if (const char *e = getenv("MC2D_SWEEP_WPB")) w0 = std::max(1, std::min(8, atoi(e)));  // tuning
-            const size_t warp_budget = 72 * 1024 / 8;
-            bool found = false;
-            for (int nb = nb_want; nb >= nb_min && !found; nb -= 4)
-                if (stride_of(nb) * (32 / G) <= warp_budget) {
-                    wpb = w0;
-                    nb_cap = nb;
-                    found = true;
-                }
-            if (!found) {  // big cells: fewer warps per SM, then one warp per cell
-                nb_cap = nb_want;
-                wpb = w0;
-                while (wpb > 1 && stride_of(nb_cap) * (32 / G) * wpb > 200 * 1024) wpb >>= 1;
-                if (stride_of(nb_cap) * (32 / G) * wpb > 200 * 1024) G = 0;
-            }
-            per_group = stride_of(nb_cap);
-        }
-    }
+    ItemLayout lay;
+    if (int rc = item_layout(ctx, &lay)) return rc;
+    const int G = lay.G, nb_cap = lay.nb_cap;
+    const size_t per_group = lay.per_group;
+    if (G) wpb = lay.wpb;
     if (!G) {
         wpb = 8;
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
