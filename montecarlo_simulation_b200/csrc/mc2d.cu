@@ -764,8 +764,8 @@ extern "C" int mc2d_download(mc2d_ctx *ctx, double *xy, int *ids, long long cap,
     return MC2D_OK;
 }
 
-// Launch shape of the kernels that work on sorted items (k_sweep_p, k_energy_p): lanes per cell, neighbour
-// slots and bytes per group, warps per CTA.  G = 0: the grid or the cells do not fit that layout.
+// Launch shape of k_energy_p (fixed-size candidate array per group): lanes per cell, neighbour slots and
+// bytes per group, warps per CTA.  G = 0: the grid or the cells do not fit that layout.
 struct ItemLayout {
     int G = 0, nb_cap = 0, wpb = 8;
     size_t per_group = 0;
@@ -775,50 +775,36 @@ static int item_layout(mc2d_ctx *ctx, ItemLayout *out) {
     const Grid &g = ctx->g;
     const int K = g.K;
     const bool ideal = ctx->prm.potential == MC2D_IDEAL;
-    const bool minimg = (g.nx < 4 || g.ny < 4);
-    int wpb = 8;
-    // Kernel choice: k_sweep_p (G lanes per cell, persistent warps over the sorted work list) unless the
-    // grid needs the per-pair minimum image or the cells are too big for its shared-memory layout; then
-    // k_sweep (one warp per cell).  G follows the expected number of candidates per cell (9 cells x mean
-    // occupancy): measured on config #4 (28 candidates), G = 4 beats 8 and 2; denser neighbourhoods
-    // (> 64 candidates) fill 8 lanes.  MC2D_SWEEP_G overrides (0 = k_sweep), for tuning and tests.
-    int G = 0, nb_cap = 0;
+    int wpb = 8, G = 0, nb_cap = 0;
     size_t per_group = 0;  // bytes between the candidate arrays of two groups
-    if (!minimg && K <= 255) {
+    if (g.nx >= 4 && g.ny >= 4 && K <= 255) {
         const double n_c = (double)std::max<long long>(ctx->n_last, 1) / std::max(1, g.ncol * g.ny);
-        G = (9.0 * n_c > 64.0) ? 8 : 4;
-        if (const char *e = getenv("MC2D_SWEEP_G")) G = atoi(e);
-        if (G != 0 && G != 4 && G != 8) FAIL(MC2D_ERR_INVALID, "MC2D_SWEEP_G must be 0, 4 or 8");
-        if (G) {
-            // A quarter warp (8 lanes x 16 B) must touch 32 distinct banks: the groups inside it sit
-            // G*16 bytes apart modulo 128 (profiles/r01f: an unpadded stride doubled every LDS.128).
-            const size_t resid = (size_t)(G * 16) % 128;
-            auto stride_of = [&](int nb) {
-                const size_t b = (size_t)(nb + K) * sizeof(double2) + (ctx->use_ids ? (size_t)K * sizeof(int) : 0);
-                size_t st = b / 128 * 128 + resid;
-                return st < b ? st + 128 : st;
-            };
-            const int nb_want = ideal ? 0 : std::min(8 * K, even_up((int)(8.0 * n_c * 1.6 + 12.0), 4));
-            const int nb_min = ideal ? 0 : std::min(8 * K, even_up((int)(8.0 * n_c * 1.25 + 8.0), 4));
-            // largest neighbour capacity that leaves 24 warps per SM (9 KB of shared memory per warp)
-            int w0 = 8;
-            if (const char *e = getenv("MC2D_SWEEP_WPB")) w0 = std::max(1, std::min(8, atoi(e)));  // tuning
-            const size_t warp_budget = 72 * 1024 / 8;
-            bool found = false;
-            for (int nb = nb_want; nb >= nb_min && !found; nb -= 4)
-                if (stride_of(nb) * (32 / G) <= warp_budget) {
-                    wpb = w0;
-                    nb_cap = nb;
-                    found = true;
-                }
-            if (!found) {  // big cells: fewer warps per SM, then one warp per cell
-                nb_cap = nb_want;
-                wpb = w0;
-                while (wpb > 1 && stride_of(nb_cap) * (32 / G) * wpb > 200 * 1024) wpb >>= 1;
-                if (stride_of(nb_cap) * (32 / G) * wpb > 200 * 1024) G = 0;
+        G = (5.0 * n_c > 40.0) ? 8 : 4;  // own cell + 4 forward neighbours
+        // A quarter warp (8 lanes x 16 B) must touch 32 distinct banks: the groups inside it sit G*16 bytes
+        // apart modulo 128 (profiles/r01_notes.md: an unpadded stride doubled every LDS.128).
+        const size_t resid = (size_t)(G * 16) % 128;
+        auto stride_of = [&](int nb) {
+            const size_t b = (size_t)(nb + K) * sizeof(double2);
+            size_t st = b / 128 * 128 + resid;
+            return st < b ? st + 128 : st;
+        };
+        // forward-neighbour slots: generous when that still leaves 32 warps per SM (7 KB per warp); an item
+        // that does not fit makes the caller fall back to k_energy_virial_g
+        const int nb_want = ideal ? 0 : std::min(4 * K, even_up((int)(4.0 * n_c * 1.8 + 12.0), 4));
+        const int nb_min = ideal ? 0 : std::min(4 * K, even_up((int)(4.0 * n_c * 1.3 + 8.0), 4));
+        const size_t warp_budget = 7 * 1024;
+        bool found = false;
+        for (int nb = nb_want; nb >= nb_min && !found; nb -= 4)
+            if (stride_of(nb) * (32 / G) <= warp_budget) {
+                nb_cap = nb;
+                found = true;
             }
-            per_group = stride_of(nb_cap);
+        if (!found) {  // big cells: fewer warps per SM
+            nb_cap = nb_want;
+            while (wpb > 1 && stride_of(nb_cap) * (32 / G) * wpb > 200 * 1024) wpb >>= 1;
+            if (stride_of(nb_cap) * (32 / G) * wpb > 200 * 1024) G = 0;
         }
+        per_group = stride_of(nb_cap);
     }
     out->G = G;
     out->nb_cap = nb_cap;
@@ -1190,7 +1176,7 @@ static int ktime_end(mc2d_ctx *ctx) {
 }
 
 template <int POT, int G, bool TRACE>
-static int launch_sweep_p(mc2d_ctx *ctx, const SweepArgs &a, int wpb, size_t smem, int nb_cap, int stride) {
+static int launch_sweep_p(mc2d_ctx *ctx, const SweepArgs &a, int wpb, size_t smem, int R) {
     static size_t smem_seen = (size_t)-1;  // per instantiation: resident CTAs per SM for this launch shape
     static int wpb_seen = 0, occ = 0;
     if (smem != smem_seen || wpb != wpb_seen) {
@@ -1203,7 +1189,7 @@ static int launch_sweep_p(mc2d_ctx *ctx, const SweepArgs &a, int wpb, size_t sme
     }
     const int want = (a.nitems + wpb - 1) / wpb;
     const int grid = std::max(1, std::min(want, ctx->num_sms * occ));
-    k_sweep_p<POT, G, TRACE><<<grid, wpb * 32, smem, ctx->stream>>>(a, nb_cap, stride);
+    k_sweep_p<POT, G, TRACE><<<grid, wpb * 32, smem, ctx->stream>>>(a, R);
     ctx->launches++;
     return MC2D_OK;
 }
@@ -1225,11 +1211,33 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
     if (per_warp * wpb > 200 * 1024) FAIL(MC2D_ERR_CELL_OVERFLOW, "cell capacity %d needs too much shared memory", K);
     const int nact = (g.ncol / 2) * (g.ny / 2);
-    ItemLayout lay;
-    if (int rc = item_layout(ctx, &lay)) return rc;
-    const int G = lay.G, nb_cap = lay.nb_cap;
-    const size_t per_group = lay.per_group;
-    if (G) wpb = lay.wpb;
+    // Kernel choice: k_sweep_p (G lanes per cell, persistent warps over the sorted work list, R candidate
+    // slots of shared memory per warp shared out by need) unless the grid needs the per-pair minimum image or
+    // one cell with all its neighbours cannot fit a warp's slots; then k_sweep (one warp per cell).
+    // MC2D_SWEEP_G overrides the lanes per cell (0 = k_sweep), for tuning and tests.
+    int G = 0, R = 0;
+    if (!minimg && K <= 255) {
+        const double n_c = (double)std::max<long long>(ctx->n_last, 1) / std::max(1, g.ncol * g.ny);
+        G = (9.0 * n_c > 64.0) ? 8 : 4;
+        if (const char *e = getenv("MC2D_SWEEP_G")) G = atoi(e);
+        if (G != 0 && G != 2 && G != 4 && G != 8) FAIL(MC2D_ERR_INVALID, "MC2D_SWEEP_G must be 0, 2, 4 or 8");
+        if (G) {
+            const size_t slot_bytes = sizeof(double2) + (ctx->use_ids ? sizeof(int) : 0);
+            const int need_max = (ideal ? 0 : 8 * K) + K;  // one cell, every slot of its neighbourhood full
+            wpb = 8;
+            if (const char *e = getenv("MC2D_SWEEP_WPB")) wpb = std::max(1, std::min(8, atoi(e)));  // tuning
+            // 6 KB per warp: 3 CTAs x 8 warps per SM (the register limit) with ~80 KB of the SM left as L1 for the
+            // count / order / position loads.  Measured on config #4: 61 us per pass for R = 320..512 slots,
+            // 67 us at 576 (the third CTA no longer fits), 79 us at 256 (one item in four runs in two batches).
+            R = (int)((6 * 1024) / slot_bytes) & ~3;  // a multiple of 4: the warps' regions stay 16-byte aligned with ids
+            if (const char *e = getenv("MC2D_SWEEP_R")) R = (std::max(need_max, atoi(e)) + 3) & ~3;  // tuning
+            if (R < need_max) {  // big cells: fewer warps per SM
+                R = (need_max + 3) & ~3;
+                while (wpb > 1 && (size_t)R * slot_bytes * wpb > 200 * 1024) wpb >>= 1;
+                if ((size_t)R * slot_bytes * wpb > 200 * 1024) G = 0;
+            }
+        }
+    }
     if (!G) {
         wpb = 8;
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
@@ -1323,19 +1331,22 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             a.trace = trace ? ctx->trace_buf.as<mc2d_trial>() : nullptr;
             a.trace_n = ctx->d_trace_n;
             a.trace_cap = trace_cap;
-            const size_t smem = G ? per_group * (32 / G) * wpb : per_warp * wpb;
+            const size_t smem = G ? (size_t)R * (sizeof(double2) + (ctx->use_ids ? sizeof(int) : 0)) * wpb : per_warp * wpb;
             int rc = ktime_begin(ctx, 0);
             if (rc) return rc;
             const int pot = ctx->prm.potential;
             DISPATCH_POT(pot, {
                 const int inst = POT * 4 + (minimg ? 2 : 0) + (trace ? 1 : 0);
                 if (persistent) {
-                    if (G == 4) {
-                        if (trace) rc = launch_sweep_p<POT, 4, true>(ctx, a, wpb, smem, nb_cap, (int)per_group);
-                        else rc = launch_sweep_p<POT, 4, false>(ctx, a, wpb, smem, nb_cap, (int)per_group);
+                    if (G == 2) {
+                        if (trace) rc = launch_sweep_p<POT, 2, true>(ctx, a, wpb, smem, R);
+                        else rc = launch_sweep_p<POT, 2, false>(ctx, a, wpb, smem, R);
+                    } else if (G == 4) {
+                        if (trace) rc = launch_sweep_p<POT, 4, true>(ctx, a, wpb, smem, R);
+                        else rc = launch_sweep_p<POT, 4, false>(ctx, a, wpb, smem, R);
                     } else {
-                        if (trace) rc = launch_sweep_p<POT, 8, true>(ctx, a, wpb, smem, nb_cap, (int)per_group);
-                        else rc = launch_sweep_p<POT, 8, false>(ctx, a, wpb, smem, nb_cap, (int)per_group);
+                        if (trace) rc = launch_sweep_p<POT, 8, true>(ctx, a, wpb, smem, R);
+                        else rc = launch_sweep_p<POT, 8, false>(ctx, a, wpb, smem, R);
                     }
                 } else if (trace) {
                     if (minimg) rc = launch_sweep_kernel<POT, true, true>(ctx, a, nblocks, wpb, smem, inst);

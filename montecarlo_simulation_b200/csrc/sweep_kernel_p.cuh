@@ -130,33 +130,6 @@ __device__ __forceinline__ double2 to_local(double2 p, double x_lo, double y_lo,
     return make_double2(ux, uy);
 }
 
-// candidate k of a cell whose neighbours did not fit in shared memory: walk the 8 cells.
-// Scalar arguments only: taking the address of the kernel parameter struct would force a copy of it
-// to the local stack in every thread.
-__device__ __noinline__ double2 slow_candidate(const double2 *pos, const int *cnt, int ghost, int nx, int ny, int K,
-                                               int lcx, int cy, int k, double x_lo, double y_lo, double Lx,
-                                               double Ly) {
-    for (int q = 0; q < 8; ++q) {
-        const int o = q + (q >= 4);
-        int ncx = lcx + o / 3 - 1, ncy = cy + o % 3 - 1;
-        if (!ghost) {
-            if (ncx < 0) ncx += nx; else if (ncx >= nx) ncx -= nx;
-        }
-        if (ncy < 0) ncy += ny; else if (ncy >= ny) ncy -= ny;
-        const int c = ncx * ny + ncy;
-        const int n = cnt[c];
-        if (k < n) {
-            const double2 p = pos[(size_t)c * K + k];
-            double ux = p.x - x_lo, uy = p.y - y_lo;
-            if (ux < -0.5 * Lx) ux += Lx; else if (ux >= 0.5 * Lx) ux -= Lx;
-            if (uy < -0.5 * Ly) uy += Ly; else if (uy >= 0.5 * Ly) uy -= Ly;
-            return make_double2(ux, uy);
-        }
-        k -= n;
-    }
-    return make_double2(1e300, 1e300);
-}
-
 template <int G>
 __device__ __forceinline__ double group_sum(double v) {
 #pragma unroll
@@ -169,6 +142,14 @@ __device__ __forceinline__ int warp_max_int(int v) {
     return v;
 }
 
+#ifndef MC2D_HOT_UNROLL
+#define MC2D_HOT_UNROLL 2
+#endif
+#define MC2D_PRAGMA_(x) _Pragma(#x)
+#define MC2D_UNROLL(n) MC2D_PRAGMA_(unroll n)
+#ifndef MC2D_SWEEPP_THREADS
+#define MC2D_SWEEPP_THREADS 256
+#endif
 #ifndef MC2D_SWEEPP_MIN_BLOCKS
 #define MC2D_SWEEPP_MIN_BLOCKS 3
 #endif
@@ -236,7 +217,7 @@ __device__ __forceinline__ void nbr_rows_cols(const Grid &g, int lcx, int cy, in
 }
 
 template <int POT, int G, bool TRACE>
-__global__ void __launch_bounds__(256, MC2D_SWEEPP_MIN_BLOCKS) k_sweep_p(SweepArgs a, int nb_cap, int stride) {
+__global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k_sweep_p(SweepArgs a, int R) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned int cred[8][7];
     constexpr int GPW = 32 / G;
@@ -244,23 +225,24 @@ __global__ void __launch_bounds__(256, MC2D_SWEEPP_MIN_BLOCKS) k_sweep_p(SweepAr
     const int K = g.K;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int gi = lane / G, sl = lane % G;
-    const int cap = nb_cap + K;  // candidate slots of one group
-    // `stride` bytes between groups: the host pads it so that a quarter warp reads 32 distinct banks
-    double2 *cand = reinterpret_cast<double2 *>(smem_raw + (size_t)(wib * GPW + gi) * stride);
-    int *own_id = reinterpret_cast<int *>(cand + cap);
+    // Shared memory: every warp owns R candidate slots (+ R ints when ids are carried).  The groups of an
+    // item take what they need from them by a prefix sum (neighbours + own + room for insertions), so the
+    // mean need, not the worst case, sets how many cells are in flight per SM.  An item that does not fit
+    // is run in batches of consecutive groups; the host guarantees that one cell always fits (R >= 9 K).
+    double2 *wslots = reinterpret_cast<double2 *>(smem_raw + (size_t)wib * R * (sizeof(double2) + (a.ids ? sizeof(int) : 0)));
+    int *wids = reinterpret_cast<int *>(wslots + R);
 
     const int nay = g.ny >> 1, npairs = g.ncol >> 1;
     const int px = a.colour & 1, py = a.colour >> 1;
     const int *perm = a.order + (size_t)a.colour * npairs * nay;
     const double hLx = 0.5 * g.Lx, hLy = 0.5 * g.Ly;
     const int src_base = gi * G;
-    const double2 far2 = make_double2(MC2D_FAR, MC2D_FAR);
     const double escale = pair_scale<POT>();
 
     unsigned int c_att[3] = {0, 0, 0}, c_acc[3] = {0, 0, 0}, c_ovf = 0;
 
     // ---- the prefetch pipeline: ticket 3 items ahead, sorted cell 2 ahead, counts 1 ahead ----
-    // The first two items of a warp are fixed (warp w takes items w and W + w of the heavy-first list; the
+    // The first two items of a warp are fixed (warp w takes items w and 2W - 1 - w of the heavy-first list; the
     // ticket counter hands out 2W, 2W + 1, ...): thousands of warps asking one address for their first
     // ticket at the same instant would queue for tens of microseconds.
     const int W = gridDim.x * wpb;
@@ -295,7 +277,7 @@ __global__ void __launch_bounds__(256, MC2D_SWEEPP_MIN_BLOCKS) k_sweep_p(SweepAr
         return m;
     };
     int it0 = blockIdx.x * wpb + wib;
-    int it1 = W + it0;
+    int it1 = 2 * W - 1 - it0;  // a heavy first item is paired with a light second one
     int it2 = __shfl_sync(FULL_MASK, ticket(), 0);
     int acy1 = load_perm(it1);
     ItemMeta m0 = load_counts(it0, load_perm(it0));
@@ -312,227 +294,221 @@ __global__ void __launch_bounds__(256, MC2D_SWEEPP_MIN_BLOCKS) k_sweep_p(SweepAr
         const int cell = lcx * g.ny + cy;
         const uint32_t cell_gid = (uint32_t)(gcx * g.ny + cy);
         const double x_lo = g.ox + gcx * g.dx, y_lo = g.oy + cy * g.dy;
-        int n_own = m0.n_own;
-        const int n_disp = n_own > 0 ? (a.disp_cell > 0 ? a.disp_cell : a.disp_mult * n_own) : 0;
-        const int n_gc = has_cell ? a.n_gc : 0;
-        const bool work = (n_disp > 0 || n_gc > 0);
-
-        // ---- stage: 8 neighbour cells -> cand[0..Ms), own cell -> cand[Ms..Ms+n_own), raw copies by
-        //      cp.async (no registers, all in flight together: one exposed memory latency per item) ----
-        int M = 0, Ms = 0;
-        if (POT != POT_IDEAL && work) {
-            M = (int)__dp4a(m0.c_lo, 0x01010101u, __dp4a(m0.c_hi, 0x01010101u, 0u));
-            if (M <= nb_cap) Ms = M;
+        const int n_own0 = m0.n_own;
+        const int n_disp0 = n_own0 > 0 ? (a.disp_cell > 0 ? a.disp_cell : a.disp_mult * n_own0) : 0;
+        const bool work0 = has_cell && (n_disp0 > 0 || a.n_gc > 0);
+        const int M = (POT != POT_IDEAL && work0)
+                          ? (int)__dp4a(m0.c_lo, 0x01010101u, __dp4a(m0.c_hi, 0x01010101u, 0u)) : 0;
+        // slots this group needs: neighbours, own particles, room for the insertions of this visit
+        const int need = work0 ? M + min(n_own0 + a.n_gc, K) : 0;
+        int incl = (sl == 0) ? need : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= d) incl += v;
         }
-        double2 *own = cand + Ms;
-        if (work) {
-            for (int s = sl; s < n_own; s += G) {
-                cp_async16(&own[s], &a.pos[(size_t)cell * K + s]);
-                if (a.ids) own_id[s] = a.ids[(size_t)cell * K + s];
-            }
-            if (Ms > 0) {  // lane sl copies neighbour cells sl, sl + G, ...
-                int col3[3], row3[3];
-                nbr_rows_cols(g, lcx, cy, col3, row3);
-                for (int q = sl; q < 8; q += G) {
-                    const int sh = 8 * (q & 3);
-                    const uint32_t below = (1u << sh) - 1u;  // bytes of the cells before q in their word
-                    const int n = (int)(((q < 4 ? m0.c_lo : m0.c_hi) >> sh) & 255u);
-                    const int pre = (q < 4) ? (int)__dp4a(m0.c_lo & below, 0x01010101u, 0u)
-                                            : (int)__dp4a(m0.c_hi & below, 0x01010101u, __dp4a(m0.c_lo, 0x01010101u, 0u));
-                    const int o = q + (q >= 4), oc = (o * 11) >> 5, orow = o - 3 * oc;
-                    const int cb = oc == 0 ? col3[0] : (oc == 1 ? col3[1] : col3[2]);
-                    const int rb = orow == 0 ? row3[0] : (orow == 1 ? row3[1] : row3[2]);
-                    const double2 *src = a.pos + (size_t)(cb + rb) * K;
-                    for (int s = 0; s < n; ++s) cp_async16(&cand[pre + s], &src[s]);
-                }
-            }
-        }
-        cp_async_wait_all();
-        __syncwarp();
-        const int ntot0 = Ms + n_own;
-        const int KM0 = warp_max_int(ntot0);  // candidate iterations of this item (all groups in lock step)
-        if (work) {  // to cell-local coordinates in place, then far points behind the list
-            for (int k = sl; k < ntot0; k += G) cand[k] = to_local(cand[k], x_lo, y_lo, g, hLx, hLy);
-            const int fill_to = min(KM0 + a.n_gc, cap);
-            for (int k = ntot0 + sl; k < fill_to; k += G) cand[k] = far2;
-        }
-        __syncwarp();
-        const bool cold = (POT != POT_IDEAL) && __any_sync(FULL_MASK, M > Ms);
-
+        // (leaders only carry a value: every lane now holds the prefix sum over the groups up to and including its own)
         double dU_total = 0.0;
-        bool dirty = false;
-        Philox4 batch = {0u, 0u, 0u, 0u};
+        int start = 0;  // slots taken by the groups of earlier batches
+        bool pending = work0;
+        do {
+            const bool work = pending && (incl - start <= R);  // a run of consecutive groups that fits
+            double2 *cand = wslots + (work ? incl - need - start : 0);
+            int *cand_id = wids + (work ? incl - need - start : 0);
+            int n_own = work ? n_own0 : 0;
+            const int n_disp = work ? n_disp0 : 0;
+            const int n_gc = work ? a.n_gc : 0;
+            const int Ms = work ? M : 0;
+            double2 *own = cand + Ms;
+            int *own_id = cand_id + Ms;
 
-        // ---- K2: displacement rounds (MC.cpp:96-123); one trial per group per round ----
-        {
-            const int T = warp_max_int(n_disp);
-            const int KC = cold ? warp_max_int(M - Ms) : 0;
-            for (int t = 0; t < T; ++t) {
-                if ((t & (G - 1)) == 0)  // sub-lane s draws the words of trial t + s of its cell's stream
-                    batch = philox4x32_10(cell_gid, MC2D_TAG_DISP | (uint32_t)(t + sl), a.sweep_lo, a.sweep_hi,
-                                          a.seed_lo, a.seed_hi);
-                const int src = src_base + (t & (G - 1));
-                const uint32_t rx = __shfl_sync(FULL_MASK, batch.x, src), ry = __shfl_sync(FULL_MASK, batch.y, src);
-                const uint32_t rz = __shfl_sync(FULL_MASK, batch.z, src), rw = __shfl_sync(FULL_MASK, batch.w, src);
-                const bool act = t < n_disp;
-                const int i = act ? (int)__umulhi(rx, (uint32_t)n_own) : 0;
-                const double2 uo = act ? own[i] : make_double2(0.0, 0.0);
-                double2 un;
-                un.x = uo.x + a.delta * (2.0 * mc2d_u01(ry) - 1.0);
-                un.y = uo.y + a.delta * (2.0 * mc2d_u01(rz) - 1.0);
-                const bool inside = act && (un.x >= 0.0 && un.x < g.dx && un.y >= 0.0 && un.y < g.dy);
-                double dE = 0.0;
-                if (POT != POT_IDEAL) {
-                    double acc = 0.0;
-                    const int self = Ms + i;
-                    // hot loop: shared memory only; slots behind a group's list hold far points
-#pragma unroll 2
-                    for (int k = sl; k < KM0; k += G) {
-                        const double2 c = cand[k];
-                        const bool notself = k != self;
-                        acc += pair_term<POT>(c.x - un.x, c.y - un.y, a.r2cut, a.pp, notself) -
-                               pair_term<POT>(c.x - uo.x, c.y - uo.y, a.r2cut, a.pp, notself);
+            // ---- stage: 8 neighbour cells -> cand[0..Ms), own cell -> cand[Ms..Ms+n_own): raw copies by
+            //      cp.async (no registers, all in flight together: one exposed memory latency per item) ----
+            if (work) {
+                for (int s = sl; s < n_own; s += G) {
+                    cp_async16(&own[s], &a.pos[(size_t)cell * K + s]);
+                    if (a.ids) own_id[s] = a.ids[(size_t)cell * K + s];
+                }
+                if (Ms > 0) {  // lane sl copies neighbour cells sl, sl + G, ...
+                    int col3[3], row3[3];
+                    nbr_rows_cols(g, lcx, cy, col3, row3);
+                    for (int q = sl; q < 8; q += G) {
+                        const int sh = 8 * (q & 3);
+                        const uint32_t below = (1u << sh) - 1u;  // bytes of the cells before q in their word
+                        const int n = (int)(((q < 4 ? m0.c_lo : m0.c_hi) >> sh) & 255u);
+                        const int pre = (q < 4) ? (int)__dp4a(m0.c_lo & below, 0x01010101u, 0u)
+                                                : (int)__dp4a(m0.c_hi & below, 0x01010101u,
+                                                              __dp4a(m0.c_lo, 0x01010101u, 0u));
+                        const int o = q + (q >= 4), oc = (o * 11) >> 5, orow = o - 3 * oc;
+                        const int cb = oc == 0 ? col3[0] : (oc == 1 ? col3[1] : col3[2]);
+                        const int rb = orow == 0 ? row3[0] : (orow == 1 ? row3[1] : row3[2]);
+                        const double2 *src = a.pos + (size_t)(cb + rb) * K;
+                        for (int s = 0; s < n; ++s) cp_async16(&cand[pre + s], &src[s]);
                     }
-                    if (cold) {
-                        for (int k = sl; k < KC; k += G) {
-                            double2 c = far2;
-                            if (inside && k < M - Ms)
-                                c = slow_candidate(a.pos, a.cnt, g.ghost, g.nx, g.ny, K, lcx, cy, k, x_lo, y_lo, g.Lx,
-                                                   g.Ly);
-                            acc += pair_term<POT>(c.x - un.x, c.y - un.y, a.r2cut, a.pp, true) -
-                                   pair_term<POT>(c.x - uo.x, c.y - uo.y, a.r2cut, a.pp, true);
+                }
+            }
+            cp_async_wait_all();
+            __syncwarp();
+            // to cell-local coordinates, in place
+            for (int k = sl; k < Ms + n_own; k += G) cand[k] = to_local(cand[k], x_lo, y_lo, g, hLx, hLy);
+            __syncwarp();
+
+            bool dirty = false;
+            Philox4 batch = {0u, 0u, 0u, 0u};
+
+            // ---- K2: displacement rounds (MC.cpp:96-123); one trial per group per round ----
+            {
+                const int T = warp_max_int(n_disp);
+                for (int t = 0; t < T; ++t) {
+                    if ((t & (G - 1)) == 0)  // sub-lane s draws the words of trial t + s of its cell's stream
+                        batch = philox4x32_10(cell_gid, MC2D_TAG_DISP | (uint32_t)(t + sl), a.sweep_lo, a.sweep_hi,
+                                              a.seed_lo, a.seed_hi);
+                    const int src = src_base + (t & (G - 1));
+                    const uint32_t rx = __shfl_sync(FULL_MASK, batch.x, src), ry = __shfl_sync(FULL_MASK, batch.y, src);
+                    const uint32_t rz = __shfl_sync(FULL_MASK, batch.z, src), rw = __shfl_sync(FULL_MASK, batch.w, src);
+                    const bool act = t < n_disp;
+                    const int i = act ? (int)__umulhi(rx, (uint32_t)n_own) : 0;
+                    const double2 uo = act ? own[i] : make_double2(0.0, 0.0);
+                    double2 un;
+                    un.x = uo.x + a.delta * (2.0 * mc2d_u01(ry) - 1.0);
+                    un.y = uo.y + a.delta * (2.0 * mc2d_u01(rz) - 1.0);
+                    const bool inside = act && (un.x >= 0.0 && un.x < g.dx && un.y >= 0.0 && un.y < g.dy);
+                    double dE = 0.0;
+                    if (POT != POT_IDEAL) {
+                        double acc = 0.0;
+                        const int self = Ms + i;
+                        const int ntot = inside ? Ms + n_own : 0;  // a trial that left the cell is rejected unseen
+                        // hot loop: shared memory only; every group runs over its own list
+                        MC2D_UNROLL(MC2D_HOT_UNROLL)
+                        for (int k = sl; k < ntot; k += G) {
+                            const double2 c = cand[k];
+                            const bool notself = k != self;
+                            acc += pair_term<POT>(c.x - un.x, c.y - un.y, a.r2cut, a.pp, notself) -
+                                   pair_term<POT>(c.x - uo.x, c.y - uo.y, a.r2cut, a.pp, notself);
+                        }
+                        dE = escale * group_sum<G>(acc);
+                    }
+                    bool accept = inside && (dE <= 0.0);
+                    if (__any_sync(FULL_MASK, inside && dE > 0.0))
+                        accept = accept || (inside && mc2d_u01(rw) < exp(-a.beta * dE));  // MC.cpp:110-115
+                    if (accept && sl == 0) own[i] = un;
+                    if (sl == 0) {
+                        c_att[0] += act;
+                        c_acc[0] += accept;
+                        if (accept) dU_total += dE;
+                    }
+                    dirty = dirty || accept;
+                    if (TRACE && sl == 0 && act) {
+                        unsigned long long slot = atomicAdd(a.trace_n, 1ull);
+                        if ((long long)slot < a.trace_cap) {
+                            mc2d_trial tr;
+                            tr.pass = a.pass; tr.cell = (int)cell_gid; tr.seq = t; tr.kind = 0;
+                            tr.accepted = accept ? 1 : 0; tr.reserved = inside ? 1 : 0;
+                            double ox_ = x_lo + uo.x, oy_ = y_lo + uo.y, nx_ = x_lo + un.x, ny_ = y_lo + un.y;
+                            if (ox_ >= g.Lx) ox_ -= g.Lx; if (oy_ >= g.Ly) oy_ -= g.Ly;
+                            if (nx_ >= g.Lx) nx_ -= g.Lx; if (ny_ >= g.Ly) ny_ -= g.Ly;
+                            tr.old_x = ox_; tr.old_y = oy_; tr.new_x = nx_; tr.new_y = ny_;
+                            tr.dE = inside ? dE : nan("");
+                            a.trace[slot] = tr;
                         }
                     }
-                    dE = escale * group_sum<G>(acc);
+                    __syncwarp();
                 }
-                bool accept = inside && (dE <= 0.0);
-                if (__any_sync(FULL_MASK, inside && dE > 0.0))
-                    accept = accept || (inside && mc2d_u01(rw) < exp(-a.beta * dE));  // MC.cpp:110-115
-                if (accept && sl == 0) own[i] = un;
-                if (sl == 0) {
-                    c_att[0] += act;
-                    c_acc[0] += accept;
-                    if (accept) dU_total += dE;
-                }
-                dirty = dirty || accept;
-                if (TRACE && sl == 0 && act) {
-                    unsigned long long slot = atomicAdd(a.trace_n, 1ull);
-                    if ((long long)slot < a.trace_cap) {
-                        mc2d_trial tr;
-                        tr.pass = a.pass; tr.cell = (int)cell_gid; tr.seq = t; tr.kind = 0;
-                        tr.accepted = accept ? 1 : 0; tr.reserved = inside ? 1 : 0;
-                        double ox_ = x_lo + uo.x, oy_ = y_lo + uo.y, nx_ = x_lo + un.x, ny_ = y_lo + un.y;
-                        if (ox_ >= g.Lx) ox_ -= g.Lx; if (oy_ >= g.Ly) oy_ -= g.Ly;
-                        if (nx_ >= g.Lx) nx_ -= g.Lx; if (ny_ >= g.Ly) ny_ -= g.Ly;
-                        tr.old_x = ox_; tr.old_y = oy_; tr.new_x = nx_; tr.new_y = ny_;
-                        tr.dE = inside ? dE : nan("");
-                        a.trace[slot] = tr;
-                    }
-                }
-                __syncwarp();
             }
-        }
 
-        // ---- K3: grand-canonical rounds (MC.cpp:189-249); insertion and deletion share one probe loop ----
-        {
-            const int T = warp_max_int(n_gc);
-            const int KC = cold ? warp_max_int(M - Ms) : 0;
-            for (int t = 0; t < T; ++t) {
-                if ((t & (G - 1)) == 0)
-                    batch = philox4x32_10(cell_gid, MC2D_TAG_GC | (uint32_t)(t + sl), a.sweep_lo, a.sweep_hi,
-                                          a.seed_lo, a.seed_hi);
-                const int src = src_base + (t & (G - 1));
-                const uint32_t rx = __shfl_sync(FULL_MASK, batch.x, src), ry = __shfl_sync(FULL_MASK, batch.y, src);
-                const uint32_t rz = __shfl_sync(FULL_MASK, batch.z, src), rw = __shfl_sync(FULL_MASK, batch.w, src);
-                const bool act = t < n_gc;
-                const double sel = mc2d_u01(rx);
-                const int kind = !act ? 0 : (sel < a.p_ins ? 1 : (sel < a.p_ins + a.p_del ? 2 : 0));
-                const bool full = (kind == 1) && (n_own >= K);
-                const bool evaluate = (kind == 1 && !full) || (kind == 2 && n_own > 0);
-                const int i = (kind == 2 && n_own > 0) ? (int)__umulhi(ry, (uint32_t)n_own) : 0;
-                double2 pt;
-                pt.x = mc2d_u01(ry) * g.dx;
-                pt.y = mc2d_u01(rz) * g.dy;
-                if (pt.x >= g.dx) pt.x = 0.0;
-                if (pt.y >= g.dy) pt.y = 0.0;
-                const double2 old = (kind == 2 && n_own > 0) ? own[i] : make_double2(0.0, 0.0);
-                const double2 probe = (kind == 1) ? pt : old;
-                double dE = 0.0;
-                if (POT != POT_IDEAL && __any_sync(FULL_MASK, evaluate)) {
-                    double acc = 0.0;
-                    const int self = (kind == 2) ? Ms + i : -1;
-                    const int KM = min(KM0 + t, cap);  // at most t insertions so far
-                    for (int k = sl; k < KM; k += G) {
-                        const double2 c = cand[k];
-                        acc += pair_term<POT>(c.x - probe.x, c.y - probe.y, a.r2cut, a.pp, k != self);
+            // ---- K3: grand-canonical rounds (MC.cpp:189-249); insertion and deletion share one probe loop ----
+            {
+                const int T = warp_max_int(n_gc);
+                for (int t = 0; t < T; ++t) {
+                    if ((t & (G - 1)) == 0)
+                        batch = philox4x32_10(cell_gid, MC2D_TAG_GC | (uint32_t)(t + sl), a.sweep_lo, a.sweep_hi,
+                                              a.seed_lo, a.seed_hi);
+                    const int src = src_base + (t & (G - 1));
+                    const uint32_t rx = __shfl_sync(FULL_MASK, batch.x, src), ry = __shfl_sync(FULL_MASK, batch.y, src);
+                    const uint32_t rz = __shfl_sync(FULL_MASK, batch.z, src), rw = __shfl_sync(FULL_MASK, batch.w, src);
+                    const bool act = t < n_gc;
+                    const double sel = mc2d_u01(rx);
+                    const int kind = !act ? 0 : (sel < a.p_ins ? 1 : (sel < a.p_ins + a.p_del ? 2 : 0));
+                    const bool full = (kind == 1) && (n_own >= K);
+                    const bool evaluate = (kind == 1 && !full) || (kind == 2 && n_own > 0);
+                    const int i = (kind == 2 && n_own > 0) ? (int)__umulhi(ry, (uint32_t)n_own) : 0;
+                    double2 pt;
+                    pt.x = mc2d_u01(ry) * g.dx;
+                    pt.y = mc2d_u01(rz) * g.dy;
+                    if (pt.x >= g.dx) pt.x = 0.0;
+                    if (pt.y >= g.dy) pt.y = 0.0;
+                    const double2 old = (kind == 2 && n_own > 0) ? own[i] : make_double2(0.0, 0.0);
+                    const double2 probe = (kind == 1) ? pt : old;
+                    double dE = 0.0;
+                    if (POT != POT_IDEAL) {
+                        double acc = 0.0;
+                        const int self = (kind == 2) ? Ms + i : -1;
+                        const int ntot = evaluate ? Ms + n_own : 0;
+                        for (int k = sl; k < ntot; k += G) {
+                            const double2 c = cand[k];
+                            acc += pair_term<POT>(c.x - probe.x, c.y - probe.y, a.r2cut, a.pp, k != self);
+                        }
+                        acc = escale * group_sum<G>(acc);
+                        dE = (kind == 2) ? -acc : acc;  // MC.cpp:200,225
                     }
-                    if (cold) {
-                        for (int k = sl; k < KC; k += G) {
-                            double2 c = far2;
-                            if (evaluate && k < M - Ms)
-                                c = slow_candidate(a.pos, a.cnt, g.ghost, g.nx, g.ny, K, lcx, cy, k, x_lo, y_lo, g.Lx,
-                                                   g.Ly);
-                            acc += pair_term<POT>(c.x - probe.x, c.y - probe.y, a.r2cut, a.pp, true);
+                    // MC.cpp:201 and :226, per-cell form
+                    const double pref = (kind == 1) ? a.zA / (double)(n_own + 1) : (double)n_own / a.zA;
+                    const double av = pref * exp(-a.beta * dE);
+                    const bool accept = evaluate && ((av >= 1.0) || (mc2d_u01(rw) < av));
+                    if (sl == 0) {
+                        if (accept && kind == 1) {
+                            own[n_own] = pt;
+                            if (a.ids) own_id[n_own] = -1;
+                        }
+                        if (accept && kind == 2) {
+                            own[i] = own[n_own - 1];
+                            if (a.ids) own_id[i] = own_id[n_own - 1];
+                        }
+                        c_att[1] += (kind == 1);
+                        c_att[2] += (kind == 2);
+                        c_acc[1] += (accept && kind == 1);
+                        c_acc[2] += (accept && kind == 2);
+                        c_ovf += full;
+                        if (accept) dU_total += dE;
+                    }
+                    if (accept) n_own += (kind == 1) ? 1 : -1;
+                    dirty = dirty || accept;
+                    if (TRACE && sl == 0 && kind > 0) {
+                        unsigned long long slot = atomicAdd(a.trace_n, 1ull);
+                        if ((long long)slot < a.trace_cap) {
+                            mc2d_trial tr;
+                            tr.pass = a.pass; tr.cell = (int)cell_gid; tr.seq = n_disp + t; tr.kind = kind;
+                            tr.accepted = accept ? 1 : 0; tr.reserved = evaluate ? 1 : 0;
+                            const double2 o_ = (kind == 2 && evaluate) ? old : make_double2(0.0, 0.0);
+                            const double2 p_ = (kind == 1) ? pt : make_double2(0.0, 0.0);
+                            double ox_ = x_lo + o_.x, oy_ = y_lo + o_.y, nx_ = x_lo + p_.x, ny_ = y_lo + p_.y;
+                            if (ox_ >= g.Lx) ox_ -= g.Lx; if (oy_ >= g.Ly) oy_ -= g.Ly;
+                            if (nx_ >= g.Lx) nx_ -= g.Lx; if (ny_ >= g.Ly) ny_ -= g.Ly;
+                            tr.old_x = ox_; tr.old_y = oy_; tr.new_x = nx_; tr.new_y = ny_;
+                            tr.dE = evaluate ? dE : nan("");
+                            a.trace[slot] = tr;
                         }
                     }
-                    acc = escale * group_sum<G>(acc);
-                    dE = (kind == 2) ? -acc : acc;  // MC.cpp:200,225
+                    __syncwarp();
                 }
-                // MC.cpp:201 and :226, per-cell form
-                const double pref = (kind == 1) ? a.zA / (double)(n_own + 1) : (double)n_own / a.zA;
-                const double av = pref * exp(-a.beta * dE);
-                const bool accept = evaluate && ((av >= 1.0) || (mc2d_u01(rw) < av));
-                if (sl == 0) {
-                    if (accept && kind == 1) {
-                        own[n_own] = pt;
-                        if (a.ids) own_id[n_own] = -1;
-                    }
-                    if (accept && kind == 2) {
-                        own[i] = own[n_own - 1];
-                        own[n_own - 1] = far2;
-                        if (a.ids) own_id[i] = own_id[n_own - 1];
-                    }
-                    c_att[1] += (kind == 1);
-                    c_att[2] += (kind == 2);
-                    c_acc[1] += (accept && kind == 1);
-                    c_acc[2] += (accept && kind == 2);
-                    c_ovf += full;
-                    if (accept) dU_total += dE;
-                }
-                if (accept) n_own += (kind == 1) ? 1 : -1;
-                dirty = dirty || accept;
-                if (TRACE && sl == 0 && kind > 0) {
-                    unsigned long long slot = atomicAdd(a.trace_n, 1ull);
-                    if ((long long)slot < a.trace_cap) {
-                        mc2d_trial tr;
-                        tr.pass = a.pass; tr.cell = (int)cell_gid; tr.seq = n_disp + t; tr.kind = kind;
-                        tr.accepted = accept ? 1 : 0; tr.reserved = evaluate ? 1 : 0;
-                        const double2 o_ = (kind == 2 && evaluate) ? old : make_double2(0.0, 0.0);
-                        const double2 p_ = (kind == 1) ? pt : make_double2(0.0, 0.0);
-                        double ox_ = x_lo + o_.x, oy_ = y_lo + o_.y, nx_ = x_lo + p_.x, ny_ = y_lo + p_.y;
-                        if (ox_ >= g.Lx) ox_ -= g.Lx; if (oy_ >= g.Ly) oy_ -= g.Ly;
-                        if (nx_ >= g.Lx) nx_ -= g.Lx; if (ny_ >= g.Ly) ny_ -= g.Ly;
-                        tr.old_x = ox_; tr.old_y = oy_; tr.new_x = nx_; tr.new_y = ny_;
-                        tr.dE = evaluate ? dE : nan("");
-                        a.trace[slot] = tr;
-                    }
-                }
-                __syncwarp();
             }
-        }
 
-        // ---- write the cell back (absolute coordinates) ----
-        if (dirty) {
-            for (int s = sl; s < n_own; s += G) {
-                const double2 u = own[s];
-                double x = x_lo + u.x, y = y_lo + u.y;
-                if (x >= g.Lx) x -= g.Lx; else if (x < 0.0) x += g.Lx;
-                if (y >= g.Ly) y -= g.Ly; else if (y < 0.0) y += g.Ly;
-                a.pos[(size_t)cell * K + s] = make_double2(x, y);
-                if (a.ids) a.ids[(size_t)cell * K + s] = own_id[s];
+            // ---- write the cell back (absolute coordinates) ----
+            if (dirty) {
+                for (int s = sl; s < n_own; s += G) {
+                    const double2 u = own[s];
+                    double x = x_lo + u.x, y = y_lo + u.y;
+                    if (x >= g.Lx) x -= g.Lx; else if (x < 0.0) x += g.Lx;
+                    if (y >= g.Ly) y -= g.Ly; else if (y < 0.0) y += g.Ly;
+                    a.pos[(size_t)cell * K + s] = make_double2(x, y);
+                    if (a.ids) a.ids[(size_t)cell * K + s] = own_id[s];
+                }
+                if (sl == 0) a.cnt[cell] = n_own;
             }
-            if (sl == 0) a.cnt[cell] = n_own;
-        }
+            __syncwarp();  // the next batch / item reuses this warp's slots
+            start = warp_max_int(work ? incl : start);
+            pending = pending && !work;
+        } while (__any_sync(FULL_MASK, pending));
         // energy change of this item, summed in lane order; the slot is private to the item
         const double dU_w = warp_sum(dU_total);
         if (lane == 0) a.partial_dU[it0] += dU_w;

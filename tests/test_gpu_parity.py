@@ -467,7 +467,7 @@ def test_sweep_kernel_variants_are_bit_identical(mc, monkeypatch):
     Lx, Ly = 61.0, 47.5
     xy = lattice(40, 32, Lx, Ly, 0.2, 3)
     res = {}
-    variants = ["0", "4", "8", "4"]
+    variants = ["0", "4", "8", "4", "2"]
     for n, G in enumerate(variants):
         monkeypatch.setenv("MC2D_SWEEP_G", G)
         with mc.Context(Lx, Ly, 2.5, T=0.9, activity=0.3, delta=0.12, seed=21) as ctx:
