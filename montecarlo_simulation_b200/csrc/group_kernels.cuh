@@ -103,12 +103,15 @@ __global__ void __launch_bounds__(256) k_energy_virial_g(V v, PairParams pp, dou
 template <int G>
 __global__ void __launch_bounds__(256) k_rebin_g(const double2 *pos_o, const int *cnt_o, const int *ids_o,
                                                  double2 *pos_n, int *cnt_n, int *ids_n, Grid gn, double sdx,
-                                                 double sdy, int *err) {
+                                                 double sdy, int w0, int n0, int w1, int n1, int *err) {
+    // this launch covers the owned cells [w0, w0 + n0) and [w1, w1 + n1) (column-major): all of them, or a
+    // slab's two boundary columns, or its interior
     constexpr int GPW = 32 / G;
     const int lane = threadIdx.x & 31;
     const int gi = lane / G, sl = lane % G;
-    const int w = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + gi;
-    const bool has = w < gn.ncol * gn.ny;
+    const int wl = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + gi;
+    const bool has = wl < n0 + n1;
+    const int w = wl < n0 ? w0 + wl : w1 + (wl - n0);
     const int lcx = gn.ghost + (has ? w / gn.ny : 0), cy = has ? w % gn.ny : 0;
     const int gcx = gn.col0 + (lcx - gn.ghost);
     const int K = gn.K;
@@ -195,6 +198,7 @@ struct HaloArgs {
     unsigned long long *myflag;    // [0] from left, [1] from right, [2] CTA ticket counter
     int col[2];                    // local column pushed to the left / right neighbour
     int push[2];
+    int signal;                    // store seq into both neighbours' flag words when the pushes are complete
     int wait[2];                   // wait for the left / right neighbour's signal
     int ny, K;
     unsigned long long seq;
@@ -221,9 +225,11 @@ __global__ void __launch_bounds__(256) k_halo_sync(HaloArgs h) {
         if (ticket == gridDim.x - 1) {
             __threadfence_system();
             h.myflag[2] = 0;  // the next launch on this stream starts from zero
-            *(volatile unsigned long long *)h.dflag[0] = h.seq;
-            *(volatile unsigned long long *)h.dflag[1] = h.seq;
-            __threadfence_system();
+            if (h.signal) {
+                *(volatile unsigned long long *)h.dflag[0] = h.seq;
+                *(volatile unsigned long long *)h.dflag[1] = h.seq;
+                __threadfence_system();
+            }
             const volatile unsigned long long *f = h.myflag;
             while ((h.wait[0] && f[0] < h.seq) || (h.wait[1] && f[1] < h.seq)) __nanosleep(32);
             __threadfence_system();

@@ -101,7 +101,8 @@ struct mc2d_ctx {
     double p_ins = 0.3, p_del = 0.3;
     int dev = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream_b = nullptr;  // slab boundary work (boundary kernels + halo pushes) next to the interior kernels
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_a = nullptr, ev_b = nullptr;
     std::string err;
 
     Grid g{};
@@ -130,7 +131,7 @@ struct mc2d_ctx {
     DevBuf partial, trace_buf;
     DevBuf order_buf;  // work order of k_sweep_p (k_order_local), rebuilt after every re-bin
     bool order_valid = false;
-    int *d_work = nullptr;  // 4 work-item ticket counters (one per colour pass of a sweep)
+    int *d_work = nullptr;  // work-item ticket counters: [p] interior / whole pass p of a sweep, [4 + p] slab boundary
     int num_sms = 0;
     DevBuf xy_in, ids_in, keys, keys_sorted, idx, idx_sorted, spos, sids, start, cub_tmp, pts, excl, outE, outC,
         outI, offsets;
@@ -316,11 +317,14 @@ extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&ctx->ev0));
     CU(cudaEventCreate(&ctx->ev1));
+    CU(cudaStreamCreateWithFlags(&ctx->stream_b, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
     CU(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
     CU(cudaMalloc(&ctx->d_energy, 4 * sizeof(double)));
     CU(cudaMalloc(&ctx->d_pair_stats, 4 * sizeof(unsigned long long)));
     CU(cudaMalloc(&ctx->d_err, 4 * sizeof(int)));
-    CU(cudaMalloc(&ctx->d_work, 4 * sizeof(int)));
+    CU(cudaMalloc(&ctx->d_work, 8 * sizeof(int)));
     CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->dev));
     CU(cudaMalloc(&ctx->d_trace_n, sizeof(unsigned long long)));
     CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -371,6 +375,9 @@ extern "C" int mc2d_destroy(mc2d_ctx *ctx) {
         if (ctx->d_trace_n) cudaFree(ctx->d_trace_n);
         if (ctx->ev0) cudaEventDestroy(ctx->ev0);
         if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+        if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+        if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+        if (ctx->stream_b) cudaStreamDestroy(ctx->stream_b);
         for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
         cudaStreamDestroy(ctx->stream);
     }
@@ -516,7 +523,8 @@ static int connect_peers(mc2d_ctx *ctx) {
     return MC2D_OK;
 }
 
-static int halo_exchange(mc2d_ctx *ctx, int buf, bool left, bool right, bool wait_left = true, bool wait_right = true) {
+static int halo_exchange(mc2d_ctx *ctx, int buf, bool left, bool right, bool wait_left = true, bool wait_right = true,
+                         bool signal = true, cudaStream_t stream = nullptr) {
 #if MC2D_HAVE_NCCL_H
     const Grid &g = ctx->g;
     if (!g.ghost) return MC2D_OK;
@@ -546,12 +554,14 @@ static int halo_exchange(mc2d_ctx *ctx, int buf, bool left, bool right, bool wai
         h.push[1] = right ? 1 : 0;
         h.wait[0] = wait_left ? 1 : 0;
         h.wait[1] = wait_right ? 1 : 0;
+        h.signal = signal ? 1 : 0;
         h.ny = g.ny;
         h.K = g.K;
-        h.seq = ++ctx->halo_seq;
+        if (signal) ++ctx->halo_seq;  // a launch that only waits waits for the sync point reached last
+        h.seq = ctx->halo_seq;
         const int total = (int)colp * (h.push[0] + h.push[1]);
         const int nblk = std::max(1, std::min(4 * ctx->num_sms, (total + 255) / 256));
-        k_halo_sync<<<nblk, 256, 0, ctx->stream>>>(h);
+        k_halo_sync<<<nblk, 256, 0, stream ? stream : ctx->stream>>>(h);
         ctx->launches++;
         return MC2D_OK;
     }
@@ -1176,7 +1186,8 @@ static int ktime_end(mc2d_ctx *ctx) {
 }
 
 template <int POT, int G, bool TRACE>
-static int launch_sweep_p(mc2d_ctx *ctx, const SweepArgs &a, int wpb, size_t smem, int R) {
+static int launch_sweep_p(mc2d_ctx *ctx, const SweepArgs &a, int wpb, size_t smem, int R, cudaStream_t stream,
+                          int reserve_ctas) {
     static size_t smem_seen = (size_t)-1;  // per instantiation: resident CTAs per SM for this launch shape
     static int wpb_seen = 0, occ = 0;
     if (smem != smem_seen || wpb != wpb_seen) {
@@ -1188,8 +1199,9 @@ static int launch_sweep_p(mc2d_ctx *ctx, const SweepArgs &a, int wpb, size_t sme
         wpb_seen = wpb;
     }
     const int want = (a.nitems + wpb - 1) / wpb;
-    const int grid = std::max(1, std::min(want, ctx->num_sms * occ));
-    k_sweep_p<POT, G, TRACE><<<grid, wpb * 32, smem, ctx->stream>>>(a, R);
+    // reserve_ctas: resident-CTA slots left free for the boundary kernel that runs next to this one
+    const int grid = std::max(1, std::min(want, ctx->num_sms * occ - reserve_ctas));
+    k_sweep_p<POT, G, TRACE><<<grid, wpb * 32, smem, stream>>>(a, R);
     ctx->launches++;
     return MC2D_OK;
 }
@@ -1261,6 +1273,41 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     ctx->kev_kind.clear();
     CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    // Slab mode with peer-memory halos: the boundary column pair of a pass (and the two boundary columns of
+    // a re-bin) run on a second stream, followed there by the push into the neighbour and the signal, while
+    // the interior runs on the main stream.  The neighbour's data and the NVLink latency arrive during the
+    // interior kernel; the wait in front of the next boundary kernel normally finds its flag already set.
+    const int npairs = g.ncol / 2;
+    bool overlap = persistent && g.ghost && ctx->have_comm && K <= 64 && npairs >= 4 && !trace;
+    if (overlap && !ctx->peers_valid)
+        if (int rc = connect_peers(ctx)) return rc;
+    overlap = overlap && ctx->p2p;
+    if (const char *e = getenv("MC2D_HALO_OVERLAP")) overlap = overlap && atoi(e) != 0;
+    cudaStream_t sa = ctx->stream, sb = ctx->stream_b;
+    auto join = [&]() -> int {  // each stream continues after everything queued so far on the other one
+        CU(cudaEventRecord(ctx->ev_a, sa));
+        CU(cudaEventRecord(ctx->ev_b, sb));
+        CU(cudaStreamWaitEvent(sb, ctx->ev_a, 0));
+        CU(cudaStreamWaitEvent(sa, ctx->ev_b, 0));
+        return MC2D_OK;
+    };
+    auto launch_rebin = [&](cudaStream_t st, const Grid &go, const Grid &gn, int nb, int w0, int n0, int w1, int n1) -> int {
+        const double2 *po = ctx->pos[ctx->cur];
+        const int *co = ctx->cnt[ctx->cur], *io = ctx->use_ids ? ctx->ids[ctx->cur] : nullptr;
+        int *in = ctx->use_ids ? ctx->ids[nb] : nullptr;
+        const int n = n0 + n1;
+        if (K <= 64 && rebin_G == 4)  // 4 lanes per new cell, 8 cells per warp
+            k_rebin_g<4><<<(n + 63) / 64, 256, 0, st>>>(po, co, io, ctx->pos[nb], ctx->cnt[nb], in, gn, gn.ox - go.ox,
+                                                         gn.oy - go.oy, w0, n0, w1, n1, ctx->d_err);
+        else if (K <= 64)  // 8 lanes per new cell, 4 cells per warp
+            k_rebin_g<8><<<(n + 31) / 32, 256, 0, st>>>(po, co, io, ctx->pos[nb], ctx->cnt[nb], in, gn, gn.ox - go.ox,
+                                                         gn.oy - go.oy, w0, n0, w1, n1, ctx->d_err);
+        else  // very populated cells: one warp per new cell (whole slab only)
+            k_rebin<<<(ncell_owned + 7) / 8, 256, 0, st>>>(po, co, io, ctx->pos[nb], ctx->cnt[nb], in, go, gn, ctx->d_err);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        return MC2D_OK;
+    };
     for (long long s = 0; s < nsweeps; ++s) {
         int order[4];
         double sx, sy;
@@ -1270,36 +1317,43 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             gn.ox = sx;
             gn.oy = sy;
             const int nb = 1 - ctx->cur;
-            if (int rc = ktime_begin(ctx, 1)) return rc;
-            if (K <= 64 && rebin_G == 4)  // 4 lanes per new cell, 8 cells per warp
-                k_rebin_g<4><<<(ncell_owned + 63) / 64, 256, 0, ctx->stream>>>(
-                    ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->use_ids ? ctx->ids[ctx->cur] : nullptr, ctx->pos[nb],
-                    ctx->cnt[nb], ctx->use_ids ? ctx->ids[nb] : nullptr, gn, gn.ox - g.ox, gn.oy - g.oy, ctx->d_err);
-            else if (K <= 64)  // 8 lanes per new cell, 4 cells per warp
-                k_rebin_g<8><<<(ncell_owned + 31) / 32, 256, 0, ctx->stream>>>(
-                    ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->use_ids ? ctx->ids[ctx->cur] : nullptr, ctx->pos[nb],
-                    ctx->cnt[nb], ctx->use_ids ? ctx->ids[nb] : nullptr, gn, gn.ox - g.ox, gn.oy - g.oy, ctx->d_err);
-            else  // very populated cells: one warp per new cell
-                k_rebin<<<(ncell_owned + 7) / 8, 256, 0, ctx->stream>>>(
-                    ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->use_ids ? ctx->ids[ctx->cur] : nullptr, ctx->pos[nb],
-                    ctx->cnt[nb], ctx->use_ids ? ctx->ids[nb] : nullptr, g, gn, ctx->d_err);
-            if (int rc = ktime_end(ctx)) return rc;
-            ctx->launches++;
-            ctx->cur = nb;
-            g = gn;
-            ctx->order_valid = false;
-            const bool even_next = (order[0] & 1) == 0;  // the first pass reads the left ghost (even columns) or the right one
-            if (g.ghost)
-                if (int rc = ktime_begin(ctx, 2)) return rc;
-            int rc = halo_exchange(ctx, ctx->cur, true, true, even_next, !even_next);
-            if (rc) return rc;
-            if (g.ghost)
+            if (overlap) {
+                int rc = join();
+                if (rc) return rc;
+                // the boundary columns read both ghosts of the old buffer: wait for the neighbours' last pushes
+                if ((rc = halo_exchange(ctx, ctx->cur, false, false, true, true, false, sb))) return rc;
+                if ((rc = launch_rebin(sb, g, gn, nb, 0, g.ny, (g.ncol - 1) * g.ny, g.ny))) return rc;
+                if ((rc = ktime_begin(ctx, 1))) return rc;
+                if ((rc = launch_rebin(sa, g, gn, nb, g.ny, (g.ncol - 2) * g.ny, 0, 0))) return rc;
                 if ((rc = ktime_end(ctx))) return rc;
+                ctx->cur = nb;
+                g = gn;
+                ctx->order_valid = false;
+                if ((rc = halo_exchange(ctx, ctx->cur, true, true, false, false, true, sb))) return rc;
+                if ((rc = join())) return rc;
+            } else {
+                int rc = ktime_begin(ctx, 1);
+                if (rc) return rc;
+                if ((rc = launch_rebin(sa, g, gn, nb, 0, ncell_owned, 0, 0))) return rc;
+                if ((rc = ktime_end(ctx))) return rc;
+                ctx->cur = nb;
+                g = gn;
+                ctx->order_valid = false;
+                const bool even_next = (order[0] & 1) == 0;  // the first pass reads the left ghost (even columns) or the right one
+                if (g.ghost)
+                    if ((rc = ktime_begin(ctx, 2))) return rc;
+                rc = halo_exchange(ctx, ctx->cur, true, true, even_next, !even_next);
+                if (rc) return rc;
+                if (g.ghost)
+                    if ((rc = ktime_end(ctx))) return rc;
+            }
         }
         if (persistent) {
+            if (overlap)  // the boundary stream may still be using the counters and the order of the last sweep
+                if (int rc = join()) return rc;
             if (!ctx->order_valid)
                 if (int rc = build_order(ctx)) return rc;
-            CU(cudaMemsetAsync(ctx->d_work, 0, 4 * sizeof(int), ctx->stream));
+            CU(cudaMemsetAsync(ctx->d_work, 0, 8 * sizeof(int), ctx->stream));
         }
         for (int p = 0; p < 4; ++p) {
             SweepArgs a;
@@ -1309,6 +1363,8 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             a.order = persistent ? ctx->order_buf.as<int>() : nullptr;
             a.work = ctx->d_work + p;
             a.nitems = nitems;
+            a.pair_lo = 0;
+            a.pair_n = npairs;
             a.g = g;
             a.pp = ctx->pp;
             a.r2cut = ctx->r2cut;
@@ -1332,30 +1388,62 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             a.trace_n = ctx->d_trace_n;
             a.trace_cap = trace_cap;
             const size_t smem = G ? (size_t)R * (sizeof(double2) + (ctx->use_ids ? sizeof(int) : 0)) * wpb : per_warp * wpb;
-            int rc = ktime_begin(ctx, 0);
-            if (rc) return rc;
             const int pot = ctx->prm.potential;
-            DISPATCH_POT(pot, {
-                const int inst = POT * 4 + (minimg ? 2 : 0) + (trace ? 1 : 0);
-                if (persistent) {
+            auto launch_items = [&](const SweepArgs &aa, cudaStream_t st, int reserve) -> int {  // k_sweep_p over aa's column pairs
+                int rc = MC2D_OK;
+                DISPATCH_POT(pot, {
                     if (G == 2) {
-                        if (trace) rc = launch_sweep_p<POT, 2, true>(ctx, a, wpb, smem, R);
-                        else rc = launch_sweep_p<POT, 2, false>(ctx, a, wpb, smem, R);
+                        if (trace) rc = launch_sweep_p<POT, 2, true>(ctx, aa, wpb, smem, R, st, reserve);
+                        else rc = launch_sweep_p<POT, 2, false>(ctx, aa, wpb, smem, R, st, reserve);
                     } else if (G == 4) {
-                        if (trace) rc = launch_sweep_p<POT, 4, true>(ctx, a, wpb, smem, R);
-                        else rc = launch_sweep_p<POT, 4, false>(ctx, a, wpb, smem, R);
+                        if (trace) rc = launch_sweep_p<POT, 4, true>(ctx, aa, wpb, smem, R, st, reserve);
+                        else rc = launch_sweep_p<POT, 4, false>(ctx, aa, wpb, smem, R, st, reserve);
                     } else {
-                        if (trace) rc = launch_sweep_p<POT, 8, true>(ctx, a, wpb, smem, R);
-                        else rc = launch_sweep_p<POT, 8, false>(ctx, a, wpb, smem, R);
+                        if (trace) rc = launch_sweep_p<POT, 8, true>(ctx, aa, wpb, smem, R, st, reserve);
+                        else rc = launch_sweep_p<POT, 8, false>(ctx, aa, wpb, smem, R, st, reserve);
                     }
-                } else if (trace) {
-                    if (minimg) rc = launch_sweep_kernel<POT, true, true>(ctx, a, nblocks, wpb, smem, inst);
-                    else rc = launch_sweep_kernel<POT, false, true>(ctx, a, nblocks, wpb, smem, inst);
-                } else {
-                    if (minimg) rc = launch_sweep_kernel<POT, true, false>(ctx, a, nblocks, wpb, smem, inst);
-                    else rc = launch_sweep_kernel<POT, false, false>(ctx, a, nblocks, wpb, smem, inst);
-                }
-            });
+                });
+                return rc;
+            };
+            int rc = MC2D_OK;
+            if (overlap) {
+                const bool left = (order[p] & 1) == 0;  // even columns active: the first owned column changes
+                const int items_per_pair = nitems / npairs;
+                if ((rc = join())) return rc;
+                // boundary pair on stream B: wait for the ghost it reads, run, push, signal
+                if ((rc = halo_exchange(ctx, ctx->cur, false, false, left, !left, false, sb))) return rc;
+                SweepArgs ab = a;
+                ab.work = ctx->d_work + 4 + p;
+                ab.pair_lo = left ? 0 : npairs - 1;
+                ab.pair_n = 1;
+                ab.nitems = items_per_pair;
+                if ((rc = launch_items(ab, sb, 0))) return rc;
+                if ((rc = halo_exchange(ctx, ctx->cur, left, !left, false, false, true, sb))) return rc;
+                // interior pairs on the main stream
+                a.pair_lo = left ? 1 : 0;
+                a.pair_n = npairs - 1;
+                a.nitems = items_per_pair * (npairs - 1);
+                if ((rc = ktime_begin(ctx, 0))) return rc;
+                if ((rc = launch_items(a, sa, (items_per_pair + wpb - 1) / wpb))) return rc;
+                if ((rc = ktime_end(ctx))) return rc;
+                continue;
+            }
+            rc = ktime_begin(ctx, 0);
+            if (rc) return rc;
+            if (persistent) {
+                rc = launch_items(a, sa, 0);
+            } else {
+                DISPATCH_POT(pot, {
+                    const int inst = POT * 4 + (minimg ? 2 : 0) + (trace ? 1 : 0);
+                    if (trace) {
+                        if (minimg) rc = launch_sweep_kernel<POT, true, true>(ctx, a, nblocks, wpb, smem, inst);
+                        else rc = launch_sweep_kernel<POT, false, true>(ctx, a, nblocks, wpb, smem, inst);
+                    } else {
+                        if (minimg) rc = launch_sweep_kernel<POT, true, false>(ctx, a, nblocks, wpb, smem, inst);
+                        else rc = launch_sweep_kernel<POT, false, false>(ctx, a, nblocks, wpb, smem, inst);
+                    }
+                });
+            }
             if (rc) return rc;
             if ((rc = ktime_end(ctx))) return rc;
             if (g.ghost) {
@@ -1369,6 +1457,11 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             }
         }
         ctx->sweep++;
+    }
+    if (overlap) {  // back to one stream; what follows (energy, download, the next call) reads both ghosts
+        int rc = join();
+        if (rc) return rc;
+        if ((rc = halo_exchange(ctx, ctx->cur, false, false, true, true, false, sa))) return rc;
     }
     k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(ctx->partial.as<double>(), 4 * nblocks, 1.0, ctx->d_energy, 1);
     ctx->launches++;

@@ -26,7 +26,8 @@ struct SweepArgs {
     int *ids;
     const int *order;  // k_sweep_p: perm[colour][column pair][rank] (k_order_local)
     int *work;         // k_sweep_p: work-item ticket counter of this pass
-    int nitems;        // k_sweep_p: work items per pass
+    int nitems;        // k_sweep_p: work items of this launch = items per column pair x pair_n
+    int pair_lo, pair_n;  // k_sweep_p: the column pairs this launch covers (a slab's boundary pair runs apart)
     Grid g;
     PairParams pp;
     double r2cut, beta, zA, delta;

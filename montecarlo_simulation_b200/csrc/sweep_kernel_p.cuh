@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         return v;
     };
     auto load_perm = [&](int item) {  // -> acy of this group's cell in `item`, or -1
-        const int p = item % npairs, j = (item / npairs) * GPW + gi;
+        const int p = a.pair_lo + item % a.pair_n, j = (item / a.pair_n) * GPW + gi;
         return (item < a.nitems && j < nay) ? perm[(size_t)p * nay + j] : -1;
     };
     auto load_counts = [&](int item, int acy) {
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         m.c_lo = m.c_hi = 0;
         if (acy >= 0) {
             int col3[3], row3[3];
-            nbr_rows_cols(g, g.ghost + 2 * (item % npairs) + px, 2 * acy + py, col3, row3);
+            nbr_rows_cols(g, g.ghost + 2 * (a.pair_lo + item % a.pair_n) + px, 2 * acy + py, col3, row3);
             m.n_own = a.cnt[col3[1] + row3[1]];
             if (POT != POT_IDEAL) {
 #pragma unroll
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         const ItemMeta m1 = load_counts(it1, acy1);
 
         const bool has_cell = m0.acy >= 0;
-        const int acx = it0 % npairs;
+        const int acx = a.pair_lo + it0 % a.pair_n;
         const int lcx = g.ghost + 2 * acx + px, cy = 2 * max(m0.acy, 0) + py, gcx = g.col0 + 2 * acx + px;
         const int cell = lcx * g.ny + cy;
         const uint32_t cell_gid = (uint32_t)(gcx * g.ny + cy);
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         } while (__any_sync(FULL_MASK, pending));
         // energy change of this item, summed in lane order; the slot is private to the item
         const double dU_w = warp_sum(dU_total);
-        if (lane == 0) a.partial_dU[it0] += dU_w;
+        if (lane == 0) a.partial_dU[(it0 / a.pair_n) * npairs + acx] += dU_w;  // the item's slot in the full list
         __syncwarp();  // the next item's staging reuses this warp's shared memory
 
         it0 = it1;
