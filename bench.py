@@ -294,10 +294,13 @@ def main():
                 "rebin_ms_per_launch": info.k_rebin_ms / max(info.k_rebin_launches, 1),
                 "halo_ms_per_sync": (info.k_halo_ms / info.k_halo_launches) if info.k_halo_launches else None,
                 "note": "path is fp64-ALU/latency bound, not HBM bound (DESIGN.md §4): low HBM fraction expected"}
-    tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tr):
+    # DRAM bytes per launch of the sweep kernel from the newest committed `ncu --set full` capture
+    import glob
+    trs = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")))
+    if trs:
         try:
-            roofline["traffic"] = json.load(open(tr)).get("k_sweep_dram_bytes_per_launch")
+            roofline["traffic"] = json.load(open(trs[-1])).get("k_sweep_dram_bytes_per_launch")
+            roofline["traffic_source"] = "profiles/" + os.path.basename(trs[-1]) + " (config #4, 1 GPU)"
         except Exception:
             pass
 

@@ -66,7 +66,7 @@ def launches(tag, path):
         for k, v in agg.items():
             fh.write("| `%s` | %d | %.1f | %.1f | %.1f%% |\n" % (k, len(v), sum(v) / len(v) / 1e3, sum(v) / 1e3,
                                                                  100 * sum(v) / tot))
-        steady = {k: v for k, v in agg.items() if k.startswith(("k_sweep", "k_rebin", "k_reduce", "k_energy", "k_sum"))}
+        steady = {k: v for k, v in agg.items() if k.startswith(("k_sweep", "k_rebin", "k_reduce", "k_energy", "k_sum", "k_order"))}
         st = sum(sum(v) for v in steady.values())
         fh.write("\nSteady-state kernels only (sweeps + reduction, upload excluded):\n\n")
         for k, v in steady.items():
