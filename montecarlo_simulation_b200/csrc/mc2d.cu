@@ -835,7 +835,7 @@ static int build_order(mc2d_ctx *ctx) {
         attr = true;
     }
     CU(ctx->order_buf.ensure(sizeof(int) * (size_t)ncell));
-    k_order_local<<<dim3(g.ncol / 2, 4), 256, smem, ctx->stream>>>(g, ctx->cnt[ctx->cur], ctx->order_buf.as<int>());
+    k_order_local<<<dim3(g.ncol / 2, 4), ORDL_WARPS * 32, smem, ctx->stream>>>(g, ctx->cnt[ctx->cur], ctx->order_buf.as<int>());
     ctx->launches++;
     ctx->order_valid = true;
     return MC2D_OK;
@@ -1296,7 +1296,11 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
         const int *co = ctx->cnt[ctx->cur], *io = ctx->use_ids ? ctx->ids[ctx->cur] : nullptr;
         int *in = ctx->use_ids ? ctx->ids[nb] : nullptr;
         const int n = n0 + n1;
-        if (K <= 64 && rebin_G == 4)  // 4 lanes per new cell, 8 cells per warp
+        const double sdx = gn.ox - go.ox, sdy = gn.oy - go.oy;
+        if (K <= 64 && rebin_G == 4 && fabs(sdx) > 1e-9 * gn.dx && fabs(sdy) > 1e-9 * gn.dy && gn.nx >= 3 && gn.ny >= 3)
+            k_rebin4<4><<<(n + 63) / 64, 256, 0, st>>>(po, co, io, ctx->pos[nb], ctx->cnt[nb], in, gn, sdx > 0 ? 1 : -1,
+                                                        sdy > 0 ? 1 : -1, w0, n0, w1, n1, ctx->d_err);
+        else if (K <= 64 && rebin_G == 4)  // 4 lanes per new cell, 8 cells per warp
             k_rebin_g<4><<<(n + 63) / 64, 256, 0, st>>>(po, co, io, ctx->pos[nb], ctx->cnt[nb], in, gn, gn.ox - go.ox,
                                                          gn.oy - go.oy, w0, n0, w1, n1, ctx->d_err);
         else if (K <= 64)  // 8 lanes per new cell, 4 cells per warp

@@ -21,37 +21,38 @@
 #pragma once
 
 // ------------------------------------------------------------------------------------------------
-// k_order_local: grid (column pairs, 4 colours), 256 threads.  perm[colour][pair][j] = row index acy
+// k_order_local: grid (column pairs, 4 colours), 128 threads.  perm[colour][pair][j] = row index acy
 // of the j-th cell of that colour in that column pair, by falling (n_own, n_own + neighbours).
 // Stable counting sort: every rank depends only on the counts, never on timing.
 // ------------------------------------------------------------------------------------------------
-constexpr int ORDL_NB = 24;  // occupancy bins (23 and above share the first)
-constexpr int ORDL_MB = 16;  // candidate-count bins of width 4 (60 and above share the first)
+constexpr int ORDL_NB = 16;  // occupancy bins (15 and above share the first)
+constexpr int ORDL_MB = 8;   // candidate-count bins of width 8 (56 and above share the first)
 constexpr int ORDL_BINS = ORDL_NB * ORDL_MB;
+constexpr int ORDL_WARPS = 4;
 
 // dynamic shared memory: 3 columns x ny counts, then nay packed (bin << 16 | rank in warp)
-__global__ void __launch_bounds__(256) k_order_local(Grid g, const int *cnt, int *perm) {
+__global__ void __launch_bounds__(ORDL_WARPS * 32) k_order_local(Grid g, const int *cnt, int *perm) {
     extern __shared__ int ol_smem[];
-    __shared__ int wc[8][ORDL_BINS];
+    __shared__ int wc[ORDL_WARPS][ORDL_BINS];
     __shared__ int bin_base[ORDL_BINS];
+    constexpr int NT = ORDL_WARPS * 32;
     const int p = blockIdx.x, colour = blockIdx.y;
     const int px = colour & 1, py = colour >> 1;
     const int nay = g.ny >> 1, npairs = g.ncol >> 1;
     const int lcx = g.ghost + 2 * p + px;
     int *ol_cnt = ol_smem, *ol_key = ol_smem + 3 * g.ny;
-    for (int i = threadIdx.x; i < 3 * g.ny; i += 256) {
-        const int c = i / g.ny, cy = i - c * g.ny;
+    for (int c = 0; c < 3; ++c) {
         int col = lcx + c - 1;
         if (!g.ghost) {
             if (col < 0) col += g.nx; else if (col >= g.nx) col -= g.nx;
         }
-        ol_cnt[i] = cnt[col * g.ny + cy];
+        for (int cy = threadIdx.x; cy < g.ny; cy += NT) ol_cnt[c * g.ny + cy] = cnt[col * g.ny + cy];
     }
-    for (int i = threadIdx.x; i < 8 * ORDL_BINS; i += 256) (&wc[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < ORDL_WARPS * ORDL_BINS; i += NT) (&wc[0][0])[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    const int per_warp = (nay + 7) / 8;  // each warp owns a contiguous range of rows (stable order)
+    const int per_warp = (nay + ORDL_WARPS - 1) / ORDL_WARPS;  // each warp owns a contiguous range of rows (stable order)
     for (int k0 = 0; k0 < per_warp; k0 += 32) {
         const int k = k0 + lane;
         const int acy = wib * per_warp + k;
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(256) k_order_local(Grid g, const int *cnt, int
             const int n = ol_cnt[g.ny + cy];
             const int m = ol_cnt[ym] + ol_cnt[cy] + ol_cnt[yp] + ol_cnt[g.ny + ym] + ol_cnt[g.ny + yp] +
                           ol_cnt[2 * g.ny + ym] + ol_cnt[2 * g.ny + cy] + ol_cnt[2 * g.ny + yp] + n;
-            b = (ORDL_NB - 1 - min(n, ORDL_NB - 1)) * ORDL_MB + (ORDL_MB - 1 - min(m >> 2, ORDL_MB - 1));
+            b = (ORDL_NB - 1 - min(n, ORDL_NB - 1)) * ORDL_MB + (ORDL_MB - 1 - min(m >> 3, ORDL_MB - 1));
         }
         const unsigned peers = __match_any_sync(FULL_MASK, b);
         const int r = __popc(peers & lt);
@@ -75,11 +76,11 @@ __global__ void __launch_bounds__(256) k_order_local(Grid g, const int *cnt, int
         if (has) ol_key[acy] = (b << 16) | (prev + r);
     }
     __syncthreads();
-    // per bin: exclusive prefix over the 8 warps, bin total -> bin_base
-    for (int b = threadIdx.x; b < ORDL_BINS; b += 256) {
+    // per bin: exclusive prefix over the warps, bin total -> bin_base
+    for (int b = threadIdx.x; b < ORDL_BINS; b += NT) {
         int run = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
+        for (int w = 0; w < ORDL_WARPS; ++w) {
             const int v = wc[w][b];
             wc[w][b] = run;
             run += v;
@@ -118,9 +119,6 @@ __global__ void __launch_bounds__(256) k_order_local(Grid g, const int *cnt, int
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_sweep_p
-// ------------------------------------------------------------------------------------------------
 // absolute position -> coordinates relative to the cell origin (x_lo, y_lo), nearest periodic image
 __device__ __forceinline__ double2 to_local(double2 p, double x_lo, double y_lo, const Grid &g, double hLx,
                                             double hLy) {
