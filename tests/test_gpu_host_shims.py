@@ -100,3 +100,36 @@ def test_input_txt_driver_and_log_formats(host_built, tmp_path):
     inp.write_text(inp.read_text().replace("ensemble GCMC", "ensemble NPT"))
     bad = subprocess.run([os.path.join(host_built, "mc2d_serial"), str(inp)], capture_output=True, text=True)
     assert bad.returncode == 1 and "not on the GPU hot path" in bad.stderr
+
+
+def test_slab_driver_and_log_formats(host_built, tmp_path):
+    """mc2d_slabs = mpi_src/main.cpp on GPU slabs (it forks one process per rank itself: no mpirun).  Same input
+    keys; thermo CSV as logging_data_mpi.cpp:56-67, LAMMPS dump with rank-as-type as logging_traj_mpi.cpp:268-303.
+    One rank here (the test box has one GPU); tools/check_multi_gpu.py and the 2-rank run in profiles/ cover more."""
+    base = tmp_path / "run"
+    inp = tmp_path / "input.txt"
+    inp.write_text("\n".join([
+        "Lx 60.0", "Ly 50.0", "N 1500", "rcut 2.5", "T 1.0", "nSteps 40", "eSteps 20", "outputFreq 20",
+        "cellUpdateFreq 10", "delta 0.1", "seed 7", "potential LennardJones", "ensemble NVT", "init lattice",
+        "out_xyz %s.xyz" % base, "out_data %s.csv" % base, ""]))
+    out = subprocess.run([os.path.join(host_built, "mc2d_slabs"), str(inp), "1"], capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Simulation completed." in out.stdout
+    rows = (tmp_path / "run.thermo.csv").read_text().strip().splitlines()
+    assert rows[0] == "timestep,N_global,rho,T,U,W,P,V"
+    assert len(rows) == 1 + 3
+    for r in rows[1:]:
+        f = r.split(",")
+        assert len(f) == 8 and int(f[1]) == 1500 and float(f[7]) == 3000.0 and float(f[3]) == 1.0
+        assert abs(float(f[2]) - 0.5) < 1e-12
+        assert abs(float(f[6]) - (0.5 * 1.0 + float(f[5]) / (2 * 3000.0))) < 1e-9  # P = rho T + W / 2V
+    dump = (tmp_path / "run.dump").read_text().splitlines()
+    assert dump[0] == "ITEM: TIMESTEP" and dump[3] == "1500" and dump[8] == "ITEM: ATOMS id type x y z"
+    assert len(dump) == 3 * (9 + 1500)
+    first = dump[9].split()
+    assert first[0] == "1" and first[1] == "1" and first[4] == "0"
+    # a bad ensemble is refused loudly
+    inp.write_text(inp.read_text().replace("ensemble NVT", "ensemble NPT"))
+    bad = subprocess.run([os.path.join(host_built, "mc2d_slabs"), str(inp), "1"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "supports NVT and GCMC" in bad.stderr
