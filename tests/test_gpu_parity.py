@@ -402,31 +402,63 @@ def test_ideal_gas_gcmc_mean_and_variance(mc, z):
 
 
 def test_lj_gcmc_matches_serial_reference_statistics(mc, oracle):
-    """<N>, <E>/N of the checkerboard GCMC vs the reference's serial GCMC (oracle port, pinned
-    bit-for-bit to the reference) at a supercritical state: agreement within 3 combined standard
+    """<N>, <E>/N and the pressure <rho T + W/2V> of the checkerboard GCMC vs the reference's serial GCMC (oracle
+    port, pinned bit-for-bit to the reference) at a supercritical state: agreement within 3 combined standard
     errors (north_star asks for 2 SE; 3 keeps the false-failure rate of this automated check < 1%)."""
     L, T, z, rcut = 20.0, 2.0, 0.08, 2.5
+    V = L * L
     calc = oracle.calc(T, 0.0, ol.LJ, rcut, z)
     start = lattice(6, 6, L, L, 0.3, 4)
     ser = oracle.mc(L, L, start, calc, rcut, 0.3, ol.GCMC, 11)
     ser.run(20000, 20000, 10)
-    _, n_s, e_s = ser.run(120000, 40, 10)
+    n_s, e_s, p_s = [], [], []
+    for _ in range(3000):  # a sample every 40 serial steps; the pressure from computePressureCellList on the snapshot
+        _, n1, e1 = ser.run(40, 40, 10)
+        n_s.append(n1[-1])
+        e_s.append(e1[-1])
+        p_s.append(oracle.pressure_celllist(calc, L, L, ser.particles()) if n1[-1] > 0 else 0.0)
+    n_s, e_s, p_s = np.array(n_s, float), np.array(e_s), np.array(p_s)
     with mc.Context(L, L, rcut, T=T, activity=z, delta=0.3, seed=3) as ctx:
         ctx.upload(start)
         ctx.run_sweeps(2000, gc_per_cell=1)
-        n_g, e_g = [], []
+        n_g, e_g, p_g = [], [], []
         for _ in range(3000):
             st = ctx.run_sweeps(4, gc_per_cell=1)
             n_g.append(st["n_particles"])
             e_g.append(st["energy"])
-        U = ctx.total_energy_virial()[0]
+            U, W, N = ctx.total_energy_virial()
+            p_g.append(N / V * T + W / (2 * V))  # thermodynamic_calculator.cpp:236-242
         assert relerr(st["energy"], U) < 1e-8
-    n_g, e_g = np.array(n_g, float), np.array(e_g)
+    n_g, e_g, p_g = np.array(n_g, float), np.array(e_g), np.array(p_g)
     se_n = math.hypot(block_se(n_s), block_se(n_g))
     assert abs(n_s.mean() - n_g.mean()) < 3 * se_n, (n_s.mean(), n_g.mean(), se_n)
     eps, epg = e_s / np.maximum(n_s, 1), e_g / np.maximum(n_g, 1)
     se_e = math.hypot(block_se(eps), block_se(epg))
     assert abs(eps.mean() - epg.mean()) < 3 * se_e, (eps.mean(), epg.mean(), se_e)
+    se_p = math.hypot(block_se(p_s), block_se(p_g))
+    assert abs(p_s.mean() - p_g.mean()) < 3 * se_p, (p_s.mean(), p_g.mean(), se_p)
+
+
+def test_batched_items_give_the_same_trajectory(mc, monkeypatch):
+    """k_sweep_p hands a warp's shared-memory slots to the cells of an item by need; an item that does not fit is
+    run in batches of consecutive cells.  Forcing the smallest legal slot count (every dense item is batched) must
+    not change a single bit of the trajectory."""
+    Lx, Ly = 61.0, 47.5
+    xy = lattice(48, 38, Lx, Ly, 0.15, 5)  # rho = 0.63: ~40 candidates per cell
+    res = []
+    for R in (None, "1"):  # "1" is raised to the minimum, 9 x cell capacity
+        if R is None:
+            monkeypatch.delenv("MC2D_SWEEP_R", raising=False)
+        else:
+            monkeypatch.setenv("MC2D_SWEEP_R", R)
+        with mc.Context(Lx, Ly, 2.5, T=1.2, activity=0.6, delta=0.1, seed=9) as ctx:
+            ctx.upload(xy)
+            st = ctx.run_sweeps(10, gc_per_cell=2)
+            res.append((ctx.download(), st))
+    (p0, s0), (p1, s1) = res
+    assert p0.shape == p1.shape and (p0 == p1).all()
+    assert s0["attempted"] == s1["attempted"] and s0["accepted"] == s1["accepted"]
+    assert relerr(s0["energy"], s1["energy"]) < 1e-12
 
 
 # ---- BASELINE sizes: size-independent properties -------------------------------------------------------------------------
