@@ -65,6 +65,8 @@ typedef struct {
     int rank, nranks; /* 1-D slab decomposition in x (replaces mpi_src Decomposition Px x Py) */
     int cell_capacity; /* particle slots per cell; 0 = choose from rcut and a dense-packing bound */
     double p_insert, p_delete; /* per GC draw (MC.cpp:194-215: 0.3 / 0.3, rest no-op); 0,0 = those defaults */
+    double cell_margin; /* cells are made >= rcut * (1 + cell_margin) wide: room for the box to shrink under
+                         * NPT volume moves without changing the cell counts (mc2d_rescale_try); 0 otherwise */
 } mc2d_params;
 
 typedef struct {
@@ -197,6 +199,18 @@ int mc2d_comm_unique_id(void *id_out /* MC2D_UNIQUE_ID_BYTES */);
 int mc2d_comm_init(mc2d_ctx *ctx, const void *unique_id);
 /* sums stats over ranks (one ncclAllReduce of a small double vector) */
 int mc2d_allreduce_stats(mc2d_ctx *ctx, mc2d_stats *inout);
+
+/* -- NPT volume move (replaces MonteCarlo::npt_move_no_cell_list, serial_src/MC.cpp:153-188) ----
+ * mc2d_rescale_try: every position is multiplied by (Lx_new/Lx, Ly_new/Ly) (SimulationBox::recenter,
+ *   initial.cpp:27-30) into the spare slot buffer and U, W of the rescaled configuration are computed
+ *   there (computeTotalEnergyCellList).  The context keeps its present configuration until
+ * mc2d_rescale_finish(accept != 0) switches to the rescaled one (running energy = U_new); accept == 0
+ *   drops it.
+ * The cell COUNTS are kept (the scaling maps cells onto cells: no re-binning), so the new cells must
+ * still be >= rcut wide: otherwise MC2D_ERR_GEOMETRY and nothing is pending — the caller re-creates
+ * the context for the new box.  Single-rank contexts only (the reference's MPI path is NVT only). */
+int mc2d_rescale_try(mc2d_ctx *ctx, double Lx_new, double Ly_new, double *U_new, double *W_new);
+int mc2d_rescale_finish(mc2d_ctx *ctx, int accept);
 
 /* -- introspection for benchmarks ------------------------------------------------------------ */
 typedef struct {

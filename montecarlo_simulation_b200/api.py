@@ -32,7 +32,7 @@ class Params(C.Structure):
                 ("f_prime", C.c_float), ("f_d_prime", C.c_float), ("kappa", C.c_float), ("alpha", C.c_float),
                 ("temperature", C.c_double), ("activity", C.c_double), ("delta", C.c_double), ("seed", C.c_uint64),
                 ("device", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("cell_capacity", C.c_int),
-                ("p_insert", C.c_double), ("p_delete", C.c_double)]
+                ("p_insert", C.c_double), ("p_delete", C.c_double), ("cell_margin", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -80,6 +80,7 @@ EXPORTS = [
     "mc2d_calc_cell_ids", "mc2d_calc_neighbor_counts", "mc2d_calc_point_energies", "mc2d_run_sweep_traced",
     "mc2d_comm_unique_id", "mc2d_comm_init", "mc2d_allreduce_stats", "mc2d_get_info", "mc2d_get_stream",
     "mc2d_synchronize", "mc2d_set_kernel_timing", "mc2d_calc_neighbor_list", "mc2d_calc_energy_virial_bruteforce",
+    "mc2d_rescale_try", "mc2d_rescale_finish",
 ]
 
 _lib = None
@@ -130,6 +131,8 @@ def load_library() -> C.CDLL:
     L.mc2d_set_kernel_timing.argtypes = [vp, i]
     L.mc2d_calc_neighbor_list.argtypes = [vp, vp, ll, ll, d, d, vp, vp, i, ip]
     L.mc2d_calc_energy_virial_bruteforce.argtypes = [vp, vp, ll, dp, dp]
+    L.mc2d_rescale_try.argtypes = [vp, d, d, dp, dp]
+    L.mc2d_rescale_finish.argtypes = [vp, i]
     _lib = L
     return L
 
@@ -209,13 +212,13 @@ class Context:
 
     def __init__(self, Lx, Ly, rcut, potential=LENNARD_JONES, T=1.0, activity=0.0, delta=0.1, seed=1, f=0.0,
                  alpha=0.0, A0=0.0, kappa=0.0, device=0, rank=0, nranks=1, cell_capacity=0, p_insert=0.0,
-                 p_delete=0.0):
+                 p_delete=0.0, cell_margin=0.0):
         self.L = load_library()
         if isinstance(potential, str):
             potential = POTENTIAL_NAMES[potential]
         fp, fdp = calc_params(f, A0, kappa)
         self.params = Params(Lx, Ly, rcut, potential, _f32(fp), _f32(fdp), _f32(kappa), _f32(alpha), T, activity,
-                             delta, seed, device, rank, nranks, cell_capacity, p_insert, p_delete)
+                             delta, seed, device, rank, nranks, cell_capacity, p_insert, p_delete, cell_margin)
         self.h = C.c_void_p()
         rc = self.L.mc2d_create(C.byref(self.params), C.byref(self.h))
         if rc:
@@ -403,6 +406,15 @@ class Context:
         s = C.c_void_p()
         self._check(self.L.mc2d_get_stream(self.h, C.byref(s)))
         return s.value
+
+    def rescale_try(self, Lx_new, Ly_new):
+        """NPT volume move, first half: (U, W) of the configuration rescaled to the new box (still pending)"""
+        U, W = C.c_double(), C.c_double()
+        self._check(self.L.mc2d_rescale_try(self.h, Lx_new, Ly_new, C.byref(U), C.byref(W)))
+        return U.value, W.value
+
+    def rescale_finish(self, accept: bool):
+        self._check(self.L.mc2d_rescale_finish(self.h, int(bool(accept))))
 
     def set_kernel_timing(self, on: bool):
         self._check(self.L.mc2d_set_kernel_timing(self.h, int(on)))

@@ -426,3 +426,24 @@ __global__ void __launch_bounds__(256) k_energy_p(const double2 *pos, const int 
         atomicAdd(&pair_stats[1], (unsigned long long)e);
     }
 }
+
+// NPT volume move: rescaled copy of the slot layout (SimulationBox::recenter, initial.cpp:27-30: p *= L_new / L_old).
+// The cell of a particle does not change (x / dx is invariant), so counts and slot order are copied.
+__global__ void __launch_bounds__(256) k_scale_slots(const double2 *pos_o, const int *cnt_o, const int *ids_o,
+                                                     double2 *pos_n, int *cnt_n, int *ids_n, int ncell, int K, double rx,
+                                                     double ry, double Lx_new, double Ly_new) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)ncell * K) return;
+    const int cell = (int)(i / K), s = (int)(i - (long long)cell * K);
+    const int n = cnt_o[cell];
+    if (s == 0) cnt_n[cell] = n;
+    if (s < n) {
+        double2 p = pos_o[i];
+        p.x *= rx;
+        p.y *= ry;
+        if (p.x >= Lx_new) p.x = nextafter(Lx_new, 0.0);  // rounding must not push a particle onto the far wall
+        if (p.y >= Ly_new) p.y = nextafter(Ly_new, 0.0);
+        pos_n[i] = p;
+        if (ids_n) ids_n[i] = ids_o[i];
+    }
+}

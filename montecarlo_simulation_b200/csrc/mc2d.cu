@@ -123,6 +123,10 @@ struct mc2d_ctx {
     bool p2p = false;                         // halo over peer memory (k_halo_sync); false: ncclSend/ncclRecv
     unsigned long long halo_seq = 0;          // sync points so far; every rank counts the same ones
     int last_G = 0;                           // lanes per cell of the last sweep launch (0: k_sweep)
+    // NPT volume move in flight (mc2d_rescale_try): the rescaled configuration sits in the spare buffer
+    bool rescale_pending = false;
+    Grid rescale_g{};
+    double rescale_Lx = 0, rescale_Ly = 0, rescale_U = 0;
 
     unsigned long long *d_counters = nullptr;  // 8
     double *d_energy = nullptr;                // [0] running, [1] U, [2] W, [3] N
@@ -292,7 +296,8 @@ extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
         ctx->p_del = p->p_delete;
     }
     Grid &g = ctx->g;
-    int rc = mc2d_sweep_grid(p->Lx, p->Ly, p->rcut, p->nranks, &g.nx, &g.ny, &g.dx, &g.dy);
+    if (!(p->cell_margin >= 0) || p->cell_margin > 1) FAIL(MC2D_ERR_INVALID, "mc2d_create: cell_margin must be in [0, 1]");
+    int rc = mc2d_sweep_grid(p->Lx, p->Ly, p->rcut * (1.0 + p->cell_margin), p->nranks, &g.nx, &g.ny, &g.dx, &g.dy);
     if (rc != MC2D_OK) {
         // The calculator hooks (reference grid) still work on such a box; only the checkerboard
         // step loop cannot run.  mc2d_upload / mc2d_run_sweeps report MC2D_ERR_GEOMETRY.
@@ -699,6 +704,7 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
                                                              ctx->d_err);
     ctx->launches++;
     ctx->have_particles = true;
+    ctx->rescale_pending = false;
     ctx->order_valid = false;
     ctx->n_last = kept;
     // The sweep counter (part of every Philox counter) is NOT reset: a context that is re-uploaded
@@ -992,6 +998,78 @@ extern "C" int mc2d_total_energy_virial(mc2d_ctx *ctx, int resync, int allreduce
 }
 
 // ------------------------------------------------------------------------------------------------
+// NPT volume move
+// ------------------------------------------------------------------------------------------------
+extern "C" int mc2d_rescale_try(mc2d_ctx *ctx, double Lx_new, double Ly_new, double *U_new, double *W_new) {
+    if (!ctx) return MC2D_ERR_INVALID;
+    if (!ctx->have_particles) FAIL(MC2D_ERR_STATE, "no particles uploaded");
+    if (ctx->prm.nranks != 1) FAIL(MC2D_ERR_INVALID, "volume moves need a single-rank context");
+    if (!(Lx_new > 0) || !(Ly_new > 0)) FAIL(MC2D_ERR_INVALID, "box lengths must be positive");
+    ctx->rescale_pending = false;
+    CU(cudaSetDevice(ctx->dev));
+    const Grid go = ctx->g;
+    Grid gn = go;
+    gn.Lx = Lx_new;
+    gn.Ly = Ly_new;
+    gn.dx = Lx_new / go.nx;
+    gn.dy = Ly_new / go.ny;
+    if (gn.dx < ctx->prm.rcut || gn.dy < ctx->prm.rcut)
+        FAIL(MC2D_ERR_GEOMETRY, "box %g x %g on %d x %d cells: cells would be narrower than rcut = %g", Lx_new, Ly_new,
+             go.nx, go.ny, ctx->prm.rcut);
+    gn.inv_dx = 1.0 / gn.dx;
+    gn.inv_dy = 1.0 / gn.dy;
+    const double rx = Lx_new / go.Lx, ry = Ly_new / go.Ly;
+    gn.ox = go.ox * rx;  // cell walls scale with the particles
+    gn.oy = go.oy * ry;
+    if (gn.ox >= gn.dx) gn.ox = 0.0;
+    if (gn.oy >= gn.dy) gn.oy = 0.0;
+    const int cur = ctx->cur, nb = 1 - cur;
+    const int ncell = go.ncs * go.ny;
+    const long long nslot = (long long)ncell * go.K;
+    k_scale_slots<<<(unsigned)((nslot + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->pos[cur], ctx->cnt[cur], ctx->use_ids ? ctx->ids[cur] : nullptr, ctx->pos[nb], ctx->cnt[nb],
+        ctx->use_ids ? ctx->ids[nb] : nullptr, ncell, go.K, rx, ry, Lx_new, Ly_new);
+    ctx->launches++;
+    // the reduction runs on the rescaled state; the context goes back to the present one afterwards
+    const double Lx_old = ctx->prm.Lx, Ly_old = ctx->prm.Ly;
+    ctx->g = gn;
+    ctx->prm.Lx = Lx_new;
+    ctx->prm.Ly = Ly_new;
+    ctx->cur = nb;
+    double U = 0, W = 0;
+    long long N = 0;
+    const int rc = energy_on_slots(ctx, &U, &W, &N, false, false);
+    ctx->g = go;
+    ctx->prm.Lx = Lx_old;
+    ctx->prm.Ly = Ly_old;
+    ctx->cur = cur;
+    if (rc) return rc;
+    ctx->rescale_pending = true;
+    ctx->rescale_g = gn;
+    ctx->rescale_Lx = Lx_new;
+    ctx->rescale_Ly = Ly_new;
+    ctx->rescale_U = U;
+    if (U_new) *U_new = U;
+    if (W_new) *W_new = W;
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_rescale_finish(mc2d_ctx *ctx, int accept) {
+    if (!ctx) return MC2D_ERR_INVALID;
+    if (!ctx->rescale_pending) FAIL(MC2D_ERR_STATE, "no volume move pending (mc2d_rescale_try first)");
+    ctx->rescale_pending = false;
+    if (!accept) return MC2D_OK;
+    CU(cudaSetDevice(ctx->dev));
+    ctx->g = ctx->rescale_g;
+    ctx->prm.Lx = ctx->rescale_Lx;
+    ctx->prm.Ly = ctx->rescale_Ly;
+    ctx->cur = 1 - ctx->cur;
+    CU(cudaMemcpyAsync(ctx->d_energy, &ctx->rescale_U, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MC2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // ThermodynamicCalculator / CellList hooks on the reference grid
 // ------------------------------------------------------------------------------------------------
 static int build_reference_csr(mc2d_ctx *ctx, const double *xy, long long n, CsrView *view) {
@@ -1209,6 +1287,7 @@ static int launch_sweep_p(mc2d_ctx *ctx, const SweepArgs &a, int wpb, size_t sme
 static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_plan *plan, mc2d_trial *trace,
                            long long trace_cap, long long *trace_n) {
     if (!ctx->have_particles) FAIL(MC2D_ERR_STATE, "no particles uploaded");
+    ctx->rescale_pending = false;  // the re-bin overwrites the spare buffer
     if (!plan || plan->disp_per_particle < 0 || plan->gc_per_cell < 0 || plan->disp_per_cell < 0 || nsweeps < 0)
         FAIL(MC2D_ERR_INVALID, "bad sweep plan");
     if (plan->disp_per_particle * 1024LL + plan->disp_per_cell + plan->gc_per_cell >= (1 << 28))

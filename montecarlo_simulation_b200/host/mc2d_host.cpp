@@ -207,7 +207,7 @@ int RNG::uniformInt(int low, int high) {
 // =================================================================================================
 namespace mc2d {
 Context::Context(double Lx, double Ly, double rcut, const PotentialSpec &pot, double T, double z, double delta,
-                 std::uint64_t seed, int device, int rank, int nranks, int cell_capacity)
+                 std::uint64_t seed, int device, int rank, int nranks, int cell_capacity, double cell_margin)
     : Lx_(Lx), Ly_(Ly) {
     mc2d_params p{};
     p.Lx = Lx;
@@ -226,6 +226,7 @@ Context::Context(double Lx, double Ly, double rcut, const PotentialSpec &pot, do
     p.rank = rank;
     p.nranks = nranks;
     p.cell_capacity = cell_capacity;
+    p.cell_margin = cell_margin;
     const int rc = mc2d_create(&p, &ctx_);
     if (rc != MC2D_OK) {
         const std::string msg = std::string(mc2d_status_string(rc)) + ": " + (ctx_ ? mc2d_last_error(ctx_) : "");
@@ -448,17 +449,23 @@ void Logging::logSimulationData(const std::vector<Particle> &particles, Simulati
 // =================================================================================================
 // MonteCarlo (serial_src/MC.cpp) on the GPU
 // =================================================================================================
+// NPT: cells 8 % wider than rcut, so the cell grid of a context serves volumes down to -14 % before the shim
+// has to re-create it (and it re-creates it when cells have grown 25 % beyond rcut)
+static constexpr double kNptCellMargin = 0.08;
+
 MonteCarlo::MonteCarlo(SimulationBox &box, std::vector<Particle> &particles, ThermodynamicCalculator &calc,
-                       double rcut, double delta, double /*delta_V*/, Ensemble ensemble, Logging &logger, RNG &rng)
-    : box_(box), particles_(particles), calc_(calc), logger_(logger), ensemble_(ensemble), rcut_(rcut),
-      delta_(delta) {
-    if (ensemble == Ensemble::NPT || ensemble == Ensemble::Gibbs)
-        throw std::runtime_error("NPT and Gibbs ensembles are not on the GPU hot path (use the reference build)");
+                       double rcut, double delta, double delta_V, Ensemble ensemble, Logging &logger, RNG &rng)
+    : box_(box), particles_(particles), calc_(calc), logger_(logger), ensemble_(ensemble), rng_(rng), rcut_(rcut),
+      delta_(delta), delta_V_(delta_V) {
+    if (ensemble == Ensemble::Gibbs)
+        throw std::runtime_error("the Gibbs ensemble is not on the GPU hot path (use the reference build)");
     // the Philox key comes from the caller's generator, so a fixed RNG seed fixes the run
     const std::uint64_t hi = static_cast<std::uint32_t>(rng.uniformInt(0, INT_MAX));
     const std::uint64_t lo = static_cast<std::uint32_t>(rng.uniformInt(0, INT_MAX));
+    seed_ = (hi << 32) | lo;
     gpu_.reset(new mc2d::Context(box.getLx(), box.getLy(), rcut, calc.potentialSpec(), calc.getTemperature(),
-                                 calc.getActivity() > 0 ? calc.getActivity() : 0.0, delta, (hi << 32) | lo));
+                                 calc.getActivity() > 0 ? calc.getActivity() : 0.0, delta, seed_, 0, 0, 1, 0,
+                                 ensemble == Ensemble::NPT ? kNptCellMargin : 0.0));
     gpu_->check(mc2d_upload(gpu_->get(), raw(particles_), nullptr, (long long)particles_.size()));  // + energy, MC.cpp:26
 }
 MonteCarlo::~MonteCarlo() = default;
@@ -504,6 +511,7 @@ int MonteCarlo::run(size_t nSteps, size_t fOutputStep, size_t fUpdateCell) {
         // the next sweep index at which the reference does something on the host (MC.cpp:62-73):
         // re-sync when step % fUpdateCell == 0, output when (step+1) % fOutputStep == 0 or at the end
         size_t stop = nSteps;
+        if (ensemble_ == Ensemble::NPT) stop = step + 1;  // a volume move may follow every sweep (MC.cpp:53-60)
         const size_t next_out = ((step / fOutputStep) + 1) * fOutputStep;       // first s+1 multiple
         const size_t next_upd = (step % fUpdateCell == 0) ? step + 1 : ((step / fUpdateCell) + 1) * fUpdateCell + 1;
         stop = std::min(stop, std::min(next_out, next_upd));
@@ -512,6 +520,11 @@ int MonteCarlo::run(size_t nSteps, size_t fOutputStep, size_t fUpdateCell) {
         simulation_step_time += st.attempted[0] + st.attempted[1] + st.attempted[2] - attempted0;
         host_stale_ = true;
         const size_t last = stop - 1;  // index of the sweep just finished
+        if (ensemble_ == Ensemble::NPT) {
+            if (rng_.uniform01() > 0.3) (void)nptMove();
+            simulation_step_time += 1;
+            gpu_->check(mc2d_get_stats(gpu_->get(), &st));
+        }
         if (last % fUpdateCell == 0) {
             double U, W;
             long long N;
@@ -527,6 +540,77 @@ int MonteCarlo::run(size_t nSteps, size_t fOutputStep, size_t fUpdateCell) {
     const long long att = st.attempted[0] + st.attempted[1] + st.attempted[2] -
                           (before.attempted[0] + before.attempted[1] + before.attempted[2]);
     return att > 0 ? static_cast<int>(acc / att) : 0;  // the reference's integer ratio (MC.cpp:76)
+}
+
+// A new context for box nb holding the configuration rescaled to it (the slow way of a volume move: download,
+// scale on the host, re-bin on a fresh cell grid).  Used when the box has left the range the present cell
+// grid can serve (cells narrower than rcut, or so wide that the sweeps waste work).
+void MonteCarlo::regrid(const SimulationBox &nb, std::unique_ptr<mc2d::Context> &out, std::vector<Particle> &scaled) {
+    sync_host();
+    scaled = particles_;
+    const double rx = nb.getLx() / box_.getLx(), ry = nb.getLy() / box_.getLy();
+    for (Particle &p : scaled) {  // SimulationBox::recenter, initial.cpp:27-30
+        p.x *= rx;
+        p.y *= ry;
+        if (p.x >= nb.getLx()) p.x = std::nextafter(nb.getLx(), 0.0);
+        if (p.y >= nb.getLy()) p.y = std::nextafter(nb.getLy(), 0.0);
+    }
+    ++regrids_;  // a fresh Philox key: the new context starts its sweep counter at zero
+    out.reset(new mc2d::Context(nb.getLx(), nb.getLy(), rcut_, calc_.potentialSpec(), calc_.getTemperature(),
+                                calc_.getActivity() > 0 ? calc_.getActivity() : 0.0, delta_,
+                                seed_ + 0x9E3779B97F4A7C15ull * (std::uint64_t)regrids_, 0, 0, 1, 0, kNptCellMargin));
+    out->check(mc2d_upload(out->get(), raw(scaled), nullptr, (long long)scaled.size()));
+}
+
+bool MonteCarlo::nptMove() {
+    const double beta = 1.0 / calc_.getTemperature(), press = calc_.getPressure();
+    const double V_o = box_.getV();
+    mc2d_stats st{};
+    gpu_->check(mc2d_get_stats(gpu_->get(), &st));
+    const double U_old = st.energy;
+    const double N = (double)st.n_particles;
+    const double lnvn = std::log(V_o) + rng_.uniform(-0.5, 0.5) * delta_V_;
+    const double V_n = std::exp(lnvn);
+    SimulationBox nb = box_;
+    nb.setV(V_n);
+    double U_new = 0, W_new = 0;
+    std::unique_ptr<mc2d::Context> fresh;
+    std::vector<Particle> scaled;
+    const int rc = mc2d_rescale_try(gpu_->get(), nb.getLx(), nb.getLy(), &U_new, &W_new);
+    if (rc == MC2D_ERR_GEOMETRY) {  // the present cell grid cannot serve the smaller box
+        regrid(nb, fresh, scaled);
+        mc2d_stats s2{};
+        fresh->check(mc2d_get_stats(fresh->get(), &s2));
+        U_new = s2.energy;
+    } else {
+        gpu_->check(rc);
+    }
+    const double arg = -beta * ((U_new - U_old) + press * (V_n - V_o) - (N + 1) * std::log(V_n / V_o) / beta);
+    const bool accept = rng_.uniform01() < std::exp(arg);  // MC.cpp:171
+    if (fresh) {
+        if (accept) {
+            gpu_ = std::move(fresh);
+            particles_ = scaled;
+            host_stale_ = false;
+        }
+    } else {
+        gpu_->check(mc2d_rescale_finish(gpu_->get(), accept ? 1 : 0));
+        if (accept) host_stale_ = true;
+    }
+    if (accept) {
+        box_ = nb;
+        // cells much wider than rcut waste pair tests: re-create the grid (no acceptance step, same configuration)
+        mc2d_info info{};
+        gpu_->check(mc2d_get_info(gpu_->get(), &info));
+        if (!fresh && std::min(info.cell_dx, info.cell_dy) > 1.25 * rcut_ && std::min(box_.getLx(), box_.getLy()) > 8 * rcut_) {
+            std::unique_ptr<mc2d::Context> finer;
+            regrid(box_, finer, scaled);
+            gpu_ = std::move(finer);
+            particles_ = scaled;
+            host_stale_ = false;
+        }
+    }
+    return accept;
 }
 
 bool MonteCarlo::stepCellList() {

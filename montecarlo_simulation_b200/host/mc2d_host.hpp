@@ -110,7 +110,8 @@ struct PotentialSpec {
 class Context {
 public:
     Context(double Lx, double Ly, double rcut, const PotentialSpec &pot, double T, double z, double delta,
-            std::uint64_t seed, int device = 0, int rank = 0, int nranks = 1, int cell_capacity = 0);
+            std::uint64_t seed, int device = 0, int rank = 0, int nranks = 1, int cell_capacity = 0,
+            double cell_margin = 0.0);
     ~Context();
     Context(const Context &) = delete;
     Context &operator=(const Context &) = delete;
@@ -224,6 +225,8 @@ public:
     double getEnergy() const;
     const std::vector<Particle> &getParticles() const;  // synchronises the caller's vector with the device
     void updateCellList();                               // no-op: device cells are always exact
+    bool nptMove();  // one volume move (MC.cpp:153-188): ln V step of width delta_V, isotropic rescaling
+    const SimulationBox &getBox() const { return box_; }
     // GPU-specific knobs
     void setGcDrawsPerCell(int n) { gc_per_cell_ = n; }
     mc2d_stats stats() const;
@@ -235,13 +238,17 @@ private:
     ThermodynamicCalculator &calc_;
     Logging &logger_;
     Ensemble ensemble_;
-    double rcut_, delta_;
+    RNG &rng_;
+    double rcut_, delta_, delta_V_;
+    std::uint64_t seed_ = 0;
+    int regrids_ = 0;  // contexts re-created because the box left the range one cell grid can serve
     int gc_per_cell_ = 1;
     long long simulation_step_time = 0;
     std::unique_ptr<mc2d::Context> gpu_;
     mutable bool host_stale_ = false;
     void sync_host() const;
     void recordObservables();
+    void regrid(const SimulationBox &nb, std::unique_ptr<mc2d::Context> &out, std::vector<Particle> &scaled);
 };
 
 // ---- mpi_src/MC_parallel.h (MonteCarloNVT_MPI) on GPU slabs ---------------------------------------------------------

@@ -39,7 +39,8 @@ int main(int argc, char *argv[]) {
         Ensemble ensemble = Ensemble::GCMC;
         if (ensemble_name == "NVT") ensemble = Ensemble::NVT;
         else if (ensemble_name == "GCMC" || ensemble_name.empty()) ensemble = Ensemble::GCMC;
-        else if (ensemble_name == "NPT" || ensemble_name == "Gibbs") {
+        else if (ensemble_name == "NPT") ensemble = Ensemble::NPT;
+        else if (ensemble_name == "Gibbs") {
             std::cerr << "Error: ensemble " << ensemble_name << " is not on the GPU hot path" << std::endl;
             return 1;
         } else {

@@ -232,6 +232,10 @@ int ref_mc_gc_move(void *h) { return static_cast<RefMC *>(h)->mc->grandCanonical
 void ref_mc_update_celllist(void *h) { static_cast<RefMC *>(h)->mc->updateCellList(); }
 double ref_mc_energy(void *h) { return static_cast<RefMC *>(h)->mc->getEnergy(); }
 int ref_mc_n(void *h) { return static_cast<int>(static_cast<RefMC *>(h)->particles.size()); }
+// NPT: the reference takes delta_V in the constructor and copies the box (MC.h:76-83); both are private
+// (reachable here through the `#define private public` above)
+void ref_mc_set_delta_V(void *h, double dv) { static_cast<RefMC *>(h)->mc->delta_V = dv; }
+double ref_mc_volume(void *h) { return static_cast<RefMC *>(h)->mc->box_.getV(); }
 void ref_mc_get_particles(void *h, double *xy) {
     auto &P = static_cast<RefMC *>(h)->particles;
     for (size_t i = 0; i < P.size(); ++i) {

@@ -268,6 +268,13 @@ class _MC:
     def n(self):
         return self._f("mc_n")(self.h)
 
+    def set_delta_V(self, dv):  # reference handle only (NPT)
+        self.lib.ref_mc_set_delta_V(self.h, dv)
+
+    @property
+    def volume(self):
+        return self.lib.ref_mc_volume(self.h)
+
     def particles(self):
         xy = np.empty((max(self.n, 1), 2), dtype=np.float64)
         self._f("mc_get_particles")(self.h, _dp(xy))
@@ -333,6 +340,10 @@ class Ref:
         L.ref_mc_energy.restype = d
         L.ref_mc_energy.argtypes = [C.c_void_p]
         L.ref_mc_get_particles.argtypes = [C.c_void_p, c_double_p]
+        if hasattr(L, "ref_mc_volume"):
+            L.ref_mc_set_delta_V.argtypes = [C.c_void_p, d]
+            L.ref_mc_volume.restype = d
+            L.ref_mc_volume.argtypes = [C.c_void_p]
         L.ref_time_mc_run.restype = d
         L.ref_time_mc_run.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, c_ll_p]
         L.ref_time_moves.restype = d

@@ -96,8 +96,8 @@ def test_input_txt_driver_and_log_formats(host_built, tmp_path):
     last = max(i for i, l in enumerate(dump) if l == "ITEM: NUMBER OF ATOMS")
     assert int(dump[last + 1]) == n and len(dump) - (last + 7) == n
     assert dump[last + 7].split()[0] == "1" and dump[last + 7].split()[3] == "0"
-    # NPT is refused loudly
-    inp.write_text(inp.read_text().replace("ensemble GCMC", "ensemble NPT"))
+    # the Gibbs ensemble is refused loudly
+    inp.write_text(inp.read_text().replace("ensemble GCMC", "ensemble Gibbs"))
     bad = subprocess.run([os.path.join(host_built, "mc2d_serial"), str(inp)], capture_output=True, text=True)
     assert bad.returncode == 1 and "not on the GPU hot path" in bad.stderr
 
@@ -133,3 +133,29 @@ def test_slab_driver_and_log_formats(host_built, tmp_path):
     inp.write_text(inp.read_text().replace("ensemble NVT", "ensemble NPT"))
     bad = subprocess.run([os.path.join(host_built, "mc2d_slabs"), str(inp), "1"], capture_output=True, text=True)
     assert bad.returncode != 0 and "supports NVT and GCMC" in bad.stderr
+
+
+def test_input_txt_driver_npt(host_built, tmp_path):
+    """`ensemble NPT` through the reference's MonteCarlo interface (MC.cpp:53-60,153-188): N stays fixed, the
+    logged volume moves, density = N / V in every row, the final dump has the final box."""
+    inp = tmp_path / "input.txt"
+    inp.write_text("\n".join([
+        "Lx 30.0", "Ly 30.0", "N 400", "rcut 2.5", "T 2.0", "P 1.0", "delta_V 0.05", "nSteps 300", "eSteps 100",
+        "outputFreq 50", "cellUpdateFreq 10", "delta 0.2", "seed 5", "potential LennardJones", "ensemble NPT",
+        "out_xyz %s" % (tmp_path / "traj.dump"), "out_data %s" % (tmp_path / "data.log"), ""]))
+    out = subprocess.run([os.path.join(host_built, "mc2d_serial"), str(inp)], capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rows = (tmp_path / "data.log").read_text().strip().splitlines()
+    vols = []
+    for l in rows:
+        f = dict(kv.strip().split(":") for kv in l.replace("\t", "").split(","))
+        assert int(f["NumberofParticles"]) == 400
+        V = float(f["Volume"])
+        assert abs(float(f["density of particles"]) - 400 / V) < 1e-4
+        vols.append(V)
+    assert len(set(vols)) > 3 and all(300.0 < v < 3000.0 for v in vols)  # started at 900 (rho = 0.44), P = 1, T = 2
+    dump = (tmp_path / "traj.dump").read_text().splitlines()
+    last = max(i for i, l in enumerate(dump) if l == "ITEM: BOX BOUNDS pp pp ff")
+    Lx = float(dump[last + 1].split()[1])
+    assert abs(Lx * Lx - vols[-1]) < 1e-3 * vols[-1]

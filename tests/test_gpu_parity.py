@@ -534,3 +534,122 @@ def test_fixed_trials_per_cell_mode(mc, oracle):
         ns = np.array([ctx.run_sweeps(3, gc_per_cell=2, disp_per_cell=2)["n_particles"] for _ in range(1500)])
     assert abs(ns.mean() - z * V) < 4 * block_se(ns) + 0.01 * math.sqrt(z * V)
     assert abs(ns.var() / (z * V) - 1.0) < 0.2
+
+
+# ---- NPT volume move ------------------------------------------------------------------------------
+
+def _npt_move(ctx, box, rng, T, P, dV):
+    """MonteCarlo::npt_move_no_cell_list (MC.cpp:153-188) through the C ABI; returns the new box and accepted"""
+    Lx, Ly = box
+    st = ctx.stats()
+    U_old, N = st["energy"], st["n_particles"]
+    V_o = Lx * Ly
+    V_n = math.exp(math.log(V_o) + rng.uniform(-0.5, 0.5) * dV)
+    ratio = Lx / Ly  # SimulationBox::setV, initial.cpp:80-87
+    Lxn, Lyn = math.sqrt(ratio * V_n), math.sqrt(V_n / ratio)
+    U_new, _ = ctx.rescale_try(Lxn, Lyn)
+    arg = -((U_new - U_old) + P * (V_n - V_o) - (N + 1) * math.log(V_n / V_o) * T) / T
+    accept = arg >= 0 or rng.random() < math.exp(arg)
+    ctx.rescale_finish(accept)
+    return ((Lxn, Lyn) if accept else box), accept
+
+
+def test_rescale_try_and_finish_parity(mc, oracle):
+    """The rescaled configuration's U and W equal the oracle's on the scaled positions; a rejected move leaves the
+    context bit for bit where it was; an accepted one continues from the scaled configuration; a box whose cells
+    would be narrower than rcut is refused."""
+    Lx, Ly = 52.0, 44.0
+    xy = lattice(36, 30, Lx, Ly, 0.2, 8)
+    calc = oracle.calc(1.0, 0.0, ol.LJ, 2.5)
+    with mc.Context(Lx, Ly, 2.5, T=1.0, delta=0.1, seed=4, cell_margin=0.08) as ctx:
+        ctx.upload(xy)
+        ctx.run_sweeps(5)
+        before = ctx.download()
+        U0 = ctx.stats()["energy"]
+        for Ln in ((53.3, 45.1), (50.1, 42.4)):  # anisotropic on purpose: the ABI takes both lengths
+            U, W = ctx.rescale_try(*Ln)
+            scaled = before * [Ln[0] / Lx, Ln[1] / Ly]
+            assert relerr(U, oracle.total_energy_celllist(calc, Ln[0], Ln[1], scaled)) < REL
+            assert relerr(W, oracle.total_virial_celllist(calc, Ln[0], Ln[1], scaled)) < REL
+            ctx.rescale_finish(False)
+            assert (ctx.download() == before).all() and ctx.stats()["energy"] == U0
+        with pytest.raises(mc.MC2DError) as e:
+            ctx.rescale_try(40.0, 44.0)  # 40 / 18 columns < rcut
+        assert e.value.status == mc.api.ERR_GEOMETRY
+        with pytest.raises(mc.MC2DError):
+            ctx.rescale_finish(True)  # nothing pending
+        Ln = (53.3, 45.1)
+        U, W = ctx.rescale_try(*Ln)
+        ctx.rescale_finish(True)
+        after = ctx.download()
+        assert (after == before * [Ln[0] / Lx, Ln[1] / Ly]).all()
+        assert ctx.stats()["energy"] == U
+        st = ctx.run_sweeps(5)
+        out = ctx.download()
+        assert relerr(st["energy"], oracle.total_energy_celllist(calc, Ln[0], Ln[1], out)) < 1e-9
+        assert out[:, 0].max() < Ln[0] and out[:, 1].max() < Ln[1] and out.min() >= 0.0
+
+
+def test_npt_ideal_gas_mean_volume(mc):
+    """Ideal gas under the reference's volume move (uniform steps in ln V, acceptance with (N+1) ln(Vn/Vo)):
+    the stationary density of V is V^N exp(-beta P V), so <V> = (N+1) T / P and Var V = (N+1) (T/P)^2."""
+    N, T, P = 200, 1.0, 2.0
+    rng = np.random.default_rng(3)
+    L0 = math.sqrt((N + 1) * T / P)
+    box = (L0 * 1.1, L0 / 1.1)
+    with mc.Context(box[0], box[1], 0.5, potential="Ideal", T=T, delta=0.2, seed=6, cell_margin=0.6) as ctx:
+        ctx.upload(rng.uniform(0, 1, (N, 2)) * box)
+        vs = []
+        for it in range(6000):
+            ctx.run_sweeps(1)
+            box, _ = _npt_move(ctx, box, rng, T, P, 0.15)
+            if it >= 500:
+                vs.append(box[0] * box[1])
+        out = ctx.download()
+    vs = np.array(vs)
+    mean, var = (N + 1) * T / P, (N + 1) * (T / P) ** 2
+    assert abs(vs.mean() - mean) < 4 * block_se(vs) + 0.002 * mean, (vs.mean(), mean, block_se(vs))
+    assert abs(vs.var() / var - 1.0) < 0.2
+    assert len(out) == N and out[:, 0].max() < box[0] and out[:, 1].max() < box[1]
+
+
+def test_npt_lj_matches_serial_reference_statistics(mc):
+    """<V> and <U>/N of an LJ fluid at fixed N, P, T: checkerboard sweeps + mc2d_rescale_* volume moves against the
+    UNMODIFIED reference's NPT loop (oracle/_ref; N displacement trials then a volume move with probability 0.7 per
+    step, MC.cpp:38-60), within 3 combined standard errors."""
+    if not ol.have_ref():
+        pytest.skip("oracle/_ref not built")
+    ref = ol.Ref()
+    if not hasattr(ref.lib, "ref_mc_volume"):
+        pytest.skip("oracle/_ref predates the NPT accessors")
+    N_side, T, P, dV, delta = 12, 2.0, 1.0, 0.08, 0.2
+    L0 = 20.0
+    start = lattice(N_side, N_side, L0, L0, 0.1, 2)
+    N = len(start)
+    ser = ref.mc(L0, L0, start, T=T, press=P, ptype=ol.LJ, rcut=2.5, delta=delta, ensemble=2, seed=17)
+    ser.set_delta_V(dV)
+    ser.run(3000, 3000, 10)
+    v_s, e_s = [], []
+    for _ in range(2500):
+        ser.run(10, 10, 10)
+        v_s.append(ser.volume)
+        e_s.append(ser.energy / N)
+    rng = np.random.default_rng(11)
+    box = (L0, L0)
+    v_g, e_g = [], []
+    with mc.Context(L0, L0, 2.5, T=T, delta=delta, seed=23, cell_margin=0.25) as ctx:
+        ctx.upload(start)
+        for it in range(3000 + 25000):
+            ctx.run_sweeps(1)
+            if rng.random() > 0.3:
+                box, _ = _npt_move(ctx, box, rng, T, P, dV)
+            if it >= 3000 and it % 10 == 9:
+                v_g.append(box[0] * box[1])
+                e_g.append(ctx.stats()["energy"] / N)
+        U = ctx.total_energy_virial()[0]
+        assert relerr(ctx.stats()["energy"], U) < 1e-8
+    v_s, e_s, v_g, e_g = map(np.array, (v_s, e_s, v_g, e_g))
+    se_v = math.hypot(block_se(v_s), block_se(v_g))
+    assert abs(v_s.mean() - v_g.mean()) < 3 * se_v, (v_s.mean(), v_g.mean(), se_v)
+    se_e = math.hypot(block_se(e_s), block_se(e_g))
+    assert abs(e_s.mean() - e_g.mean()) < 3 * se_e, (e_s.mean(), e_g.mean(), se_e)
