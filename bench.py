@@ -68,7 +68,8 @@ def workload(n_gpus, rank, particles_per_gpu=None):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe): NVML every 2 ms, or
+    nvidia-smi every 0.2 s when pynvml is missing."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -78,14 +79,39 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], threading.Event()
 
+    def _nvml(self):
+        """NVML handle for fast sampling (one query takes microseconds; nvidia-smi takes tens of milliseconds,
+        longer than a timed step)"""
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            return nv, nv.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            return None, None
+
     def run(self):
+        nv, h = self._nvml()
         while not self.stop_flag.is_set():
             try:
+                if nv is not None:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    act = lambda bit: "Active" if (r & bit) else "Not Active"
+                    self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                      str(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)),
+                                      str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0),
+                                      act(nv.nvmlClocksThrottleReasonHwSlowdown),
+                                      act(nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                                      act(nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                                      act(nv.nvmlClocksThrottleReasonSwPowerCap)])
+                    self.stop_flag.wait(0.002)
+                    continue
                 out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                                "--format=csv,noheader,nounits"], timeout=5).decode().strip()
                 self.rows.append([f.strip() for f in out.split(",")])
             except Exception:
-                pass
+                nv = None
             self.stop_flag.wait(0.2)
 
     def summary(self):

@@ -66,7 +66,9 @@ typedef struct {
     int cell_capacity; /* particle slots per cell; 0 = choose from rcut and a dense-packing bound */
     double p_insert, p_delete; /* per GC draw (MC.cpp:194-215: 0.3 / 0.3, rest no-op); 0,0 = those defaults */
     double cell_margin; /* cells are made >= rcut * (1 + cell_margin) wide: room for the box to shrink under
-                         * NPT volume moves without changing the cell counts (mc2d_rescale_try); 0 otherwise */
+                         * NPT volume moves without changing the cell counts (mc2d_rescale_try), or fuller cells
+                         * for short-range potentials.  0: cells of rcut.  -1: chosen at the first upload so that
+                         * a cell holds ~2.5 particles (single rank; never narrower than rcut) */
 } mc2d_params;
 
 typedef struct {

@@ -653,3 +653,24 @@ def test_npt_lj_matches_serial_reference_statistics(mc):
     assert abs(v_s.mean() - v_g.mean()) < 3 * se_v, (v_s.mean(), v_g.mean(), se_v)
     se_e = math.hypot(block_se(e_s), block_se(e_g))
     assert abs(e_s.mean() - e_g.mean()) < 3 * se_e, (e_s.mean(), e_g.mean(), se_e)
+
+
+def test_auto_cell_width_for_short_range_potentials(mc, oracle):
+    """cell_margin = -1: at the first upload the cells are widened until they hold ~2.5 particles (never below rcut).
+    WCA at rho = 0.5 has 0.63 particles per rcut-cell; the wider grid must give the same energies and keep the
+    bookkeeping exact."""
+    L, rc = 120.0, 2.0 ** (1.0 / 6.0)
+    xy = lattice(84, 84, L, L, 0.15, 6)
+    calc = oracle.calc(1.0, 0.0, ol.WCA, rc)
+    with mc.Context(L, L, rc, potential="WCA", T=1.0, delta=0.1, seed=2, cell_margin=-1.0) as ctx, \
+            mc.Context(L, L, rc, potential="WCA", T=1.0, delta=0.1, seed=2) as ref:
+        ctx.upload(xy)
+        ref.upload(xy)
+        a, b = ctx.info(), ref.info()
+        assert b.nx == 106 and a.nx < 70 and a.cell_dx >= rc and a.nx % 2 == 0  # ~2 rcut wide
+        U, W, N = ctx.total_energy_virial()
+        Ur, Wr, _ = ref.total_energy_virial()
+        assert relerr(U, Ur) < REL and relerr(W, Wr) < REL
+        st = ctx.run_sweeps(10, gc_per_cell=1)
+        out = ctx.download()
+        assert relerr(st["energy"], oracle.total_energy_celllist(calc, L, L, out)) < 1e-9

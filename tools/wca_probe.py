@@ -10,7 +10,8 @@ n = int(os.environ.get("AB_PARTICLES", "1000000"))
 z = float(os.environ.get("WCA_Z", "1.0"))
 wl = bench.workload(1, 0, n)
 rc = 2.0 ** (1.0 / 6.0)
-with m.Context(wl["L"], wl["L"], rc, potential="WCA", T=1.0, activity=z, delta=0.1, seed=42) as ctx:
+with m.Context(wl["L"], wl["L"], rc, potential="WCA", T=1.0, activity=z, delta=0.1, seed=42,
+               cell_margin=float(os.environ.get("WCA_MARGIN", "0"))) as ctx:
     ctx.upload(wl["xy"])
     for label, plan in (("NVT", dict(gc_per_cell=0)), ("GCMC", dict(gc_per_cell=1))):
         ctx.run_sweeps(50, **plan)
