@@ -123,6 +123,7 @@ struct mc2d_ctx {
     bool p2p = false;                         // halo over peer memory (k_halo_sync); false: ncclSend/ncclRecv
     unsigned long long halo_seq = 0;          // sync points so far; every rank counts the same ones
     int last_G = 0;                           // lanes per cell of the last sweep launch (0: k_sweep)
+    int fuse_passes = 1;                      // MC2D_SWEEP_FUSE=0: one launch per colour pass (A-B tests)
     bool auto_margin = false;                 // cell_margin = -1: the cell width is chosen at the first upload
     // NPT volume move in flight (mc2d_rescale_try): the rescaled configuration sits in the spare buffer
     bool rescale_pending = false;
@@ -1308,7 +1309,15 @@ static int launch_sweep_p(mc2d_ctx *ctx, const SweepArgs &a, int wpb, size_t sme
     const int want = (a.nitems + wpb - 1) / wpb;
     // reserve_ctas: resident-CTA slots left free for the boundary kernel that runs next to this one
     const int grid = std::max(1, std::min(want, ctx->num_sms * occ - reserve_ctas));
-    k_sweep_p<POT, G, TRACE><<<grid, wpb * 32, smem, stream>>>(a, R);
+    if (a.npass > 1) {  // all passes of a sweep in one launch: the grid barrier needs a cooperative launch
+        SweepArgs aa = a;
+        int Rv = R;
+        void *kargs[] = {&aa, &Rv};
+        CU(cudaLaunchCooperativeKernel((const void *)k_sweep_p<POT, G, TRACE>, dim3(grid), dim3(wpb * 32), kargs, smem,
+                                       stream));
+    } else {
+        k_sweep_p<POT, G, TRACE><<<grid, wpb * 32, smem, stream>>>(a, R);
+    }
     ctx->launches++;
     return MC2D_OK;
 }
@@ -1379,6 +1388,7 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     int rebin_G = 4;
     if (const char *e = getenv("MC2D_REBIN_G")) rebin_G = atoi(e);
     ctx->kev_kind.clear();
+    if (const char *e = getenv("MC2D_SWEEP_FUSE")) ctx->fuse_passes = atoi(e);
     CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     // Slab mode with peer-memory halos: the boundary column pair of a pass (and the two boundary columns of
@@ -1467,7 +1477,10 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
                 if (int rc = build_order(ctx)) return rc;
             CU(cudaMemsetAsync(ctx->d_work, 0, 8 * sizeof(int), ctx->stream));
         }
-        for (int p = 0; p < 4; ++p) {
+        // single rank / no overlap: the four passes of a sweep go out as ONE cooperative launch (grid barrier between
+        // colours); MC2D_SWEEP_FUSE=0 launches them one by one
+        const bool fuse = persistent && !overlap && !g.ghost && ctx->fuse_passes;
+        for (int p = 0; p < (fuse ? 1 : 4); ++p) {
             SweepArgs a;
             a.pos = ctx->pos[ctx->cur];
             a.cnt = ctx->cnt[ctx->cur];
@@ -1477,6 +1490,9 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             a.nitems = nitems;
             a.pair_lo = 0;
             a.pair_n = npairs;
+            a.npass = fuse ? 4 : 1;
+            for (int q = 0; q < 4; ++q) a.colours[q] = order[q];
+            a.dU_stride = nblocks;
             a.g = g;
             a.pp = ctx->pp;
             a.r2cut = ctx->r2cut;
@@ -1540,7 +1556,7 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
                 if ((rc = ktime_end(ctx))) return rc;
                 continue;
             }
-            rc = ktime_begin(ctx, 0);
+            rc = ktime_begin(ctx, fuse ? 3 : 0);  // 3: one launch = the four passes of a sweep
             if (rc) return rc;
             if (persistent) {
                 rc = launch_items(a, sa, 0);
@@ -1593,9 +1609,9 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
         for (size_t i = 0; i < ctx->kev_kind.size(); ++i) {
             float t = 0;
             CU(cudaEventElapsedTime(&t, ctx->kev[2 * i], ctx->kev[2 * i + 1]));
-            if (ctx->kev_kind[i] == 0) {
+            if (ctx->kev_kind[i] == 0 || ctx->kev_kind[i] == 3) {
                 ctx->k_sweep_ms += t;
-                ctx->k_sweep_launches++;
+                ctx->k_sweep_launches += ctx->kev_kind[i] == 3 ? 4 : 1;  // counted in colour passes
             } else if (ctx->kev_kind[i] == 1) {
                 ctx->k_rebin_ms += t;
                 ctx->k_rebin_launches++;

@@ -28,6 +28,9 @@ struct SweepArgs {
     int *work;         // k_sweep_p: work-item ticket counter of this pass
     int nitems;        // k_sweep_p: work items of this launch = items per column pair x pair_n
     int pair_lo, pair_n;  // k_sweep_p: the column pairs this launch covers (a slab's boundary pair runs apart)
+    int npass;            // k_sweep_p: colour passes done by this launch: 1, or 4 with a grid barrier in between
+    int colours[4];       //            their colours (npass > 1); pass p uses work[p] and partial_dU + p * dU_stride
+    int dU_stride;
     Grid g;
     PairParams pp;
     double r2cut, beta, zA, delta;
@@ -59,6 +62,12 @@ __device__ __forceinline__ double fast_rcp(double x) {
     }
     return r;
 }
+
+// Metropolis test in log form.  "u < exp(-x)" (MC.cpp:110-115,201,226) is "-ln u > x": the transcendental then
+// depends on the random word only, not on the energy difference, so k_sweep_p evaluates it off the critical
+// path (once per batch of Philox words, one lane per trial) and the decision itself is one compare.  Both sweep
+// kernels use exactly these expressions, so they take the same decisions.
+__device__ __forceinline__ double mc2d_exp_variate(uint32_t w) { return -log(mc2d_u01(w)); }
 
 // pair energy with the inclusive cutoff; LJ / WCA take the fast reciprocal
 template <int POT>
@@ -215,7 +224,7 @@ __global__ void __launch_bounds__(256, MC2D_SWEEP_MIN_BLOCKS) k_sweep(SweepArgs 
                         }
                         dE = warp_sum(acc);
                     }
-                    accept = (dE <= 0.0) || (mc2d_u01(r.w) < exp(-a.beta * dE));  // MC.cpp:110-115
+                    accept = a.beta * dE < mc2d_exp_variate(r.w);  // MC.cpp:110-115 in log form (below)
                     if (accept) {
                         __syncwarp();
                         if (lane == 0) own[i] = un;
@@ -278,8 +287,8 @@ __global__ void __launch_bounds__(256, MC2D_SWEEP_MIN_BLOCKS) k_sweep(SweepArgs 
                             dE = warp_sum(acc);
                         }
                         evaluated = true;
-                        const double av = a.zA / (double)(n_own + 1) * exp(-a.beta * dE);  // MC.cpp:201
-                        accept = (av >= 1.0) || (mc2d_u01(r.w) < av);
+                        // MC.cpp:201: u < z A / (n + 1) exp(-beta dU), in log form
+                        accept = a.beta * dE - (log(a.zA) - log((double)(n_own + 1))) < mc2d_exp_variate(r.w);
                         if (accept) {
                             __syncwarp();
                             if (lane == 0) {
@@ -311,8 +320,8 @@ __global__ void __launch_bounds__(256, MC2D_SWEEP_MIN_BLOCKS) k_sweep(SweepArgs 
                             dE = -warp_sum(acc);  // MC.cpp:225
                         }
                         evaluated = true;
-                        const double av = (double)n_own / a.zA * exp(-a.beta * dE);  // MC.cpp:226
-                        accept = (av >= 1.0) || (mc2d_u01(r.w) < av);
+                        // MC.cpp:226: u < n / (z A) exp(-beta dU), in log form
+                        accept = a.beta * dE - (log((double)n_own) - log(a.zA)) < mc2d_exp_variate(r.w);
                         if (accept) {
                             __syncwarp();
                             if (lane == 0) {

@@ -19,6 +19,7 @@
 // The energy change of a pass is accumulated per ITEM (fixed composition, fixed order inside the
 // warp), so the running energy stays reproducible although items are scheduled dynamically.
 #pragma once
+#include <cooperative_groups.h>
 
 // ------------------------------------------------------------------------------------------------
 // k_order_local: grid (column pairs, 4 colours), 128 threads.  perm[colour][pair][j] = row index acy
@@ -218,11 +219,17 @@ template <int POT, int G, bool TRACE>
 __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k_sweep_p(SweepArgs a, int R) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned int cred[8][7];
+    __shared__ double lntab[258];  // ln k for the insertion / deletion prefactors (K <= 255)
     constexpr int GPW = 32 / G;
     const Grid &g = a.g;
     const int K = g.K;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int gi = lane / G, sl = lane % G;
+    if (a.n_gc > 0) {
+        for (int k = threadIdx.x; k < 258; k += blockDim.x) lntab[k] = log((double)max(k, 1));
+        __syncthreads();
+    }
+    const double ln_zA = log(a.zA);
     // Shared memory: every warp owns R candidate slots (+ R ints when ids are carried).  The groups of an
     // item take what they need from them by a prefix sum (neighbours + own + room for insertions), so the
     // mean need, not the worst case, sets how many cells are in flight per SM.  An item that does not fit
@@ -231,22 +238,29 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
     int *wids = reinterpret_cast<int *>(wslots + R);
 
     const int nay = g.ny >> 1, npairs = g.ncol >> 1;
-    const int px = a.colour & 1, py = a.colour >> 1;
-    const int *perm = a.order + (size_t)a.colour * npairs * nay;
+    // per colour pass (a launch does one pass, or all four of a sweep with a grid barrier in between: a launch and
+    // its ramp-up cost ~8 us, a sixth of a pass of config #4)
+    int px = 0, py = 0, pass_no = a.pass;
+    const int *perm = a.order;
+    int *work = a.work;
+    double *pdU = a.partial_dU;
     const double hLx = 0.5 * g.Lx, hLy = 0.5 * g.Ly;
     const int src_base = gi * G;
     const double escale = pair_scale<POT>();
 
     unsigned int c_att[3] = {0, 0, 0}, c_acc[3] = {0, 0, 0}, c_ovf = 0;
 
-    // ---- the prefetch pipeline: ticket 3 items ahead, sorted cell 2 ahead, counts 1 ahead ----
-    // The first two items of a warp are fixed (warp w takes items w and 2W - 1 - w of the heavy-first list; the
-    // ticket counter hands out 2W, 2W + 1, ...): thousands of warps asking one address for their first
-    // ticket at the same instant would queue for tens of microseconds.
+    // ---- work distribution and prefetch ----
+    // Warp w starts with item w of the heavy-first list (a fixed first item: thousands of warps asking one address
+    // for a ticket at the same instant would queue for tens of microseconds); every further item comes from the
+    // ticket counter, asked for only when the previous item starts (late binding: a warp that drew a heavy item
+    // simply takes fewer items, the tail is one light item long).  The index chain of the next item is fetched in
+    // the shadow of the current one: ticket at the top, sorted cell after the staging wait, the 9 counts after
+    // the displacement rounds.
     const int W = gridDim.x * wpb;
     auto ticket = [&]() {
         int v = 0;
-        if (lane == 0) v = 2 * W + atomicAdd(a.work, 1);
+        if (lane == 0) v = W + atomicAdd(work, 1);
         return v;
     };
     auto load_perm = [&](int item) {  // -> acy of this group's cell in `item`, or -1
@@ -274,17 +288,24 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         }
         return m;
     };
+  for (int ps = 0; ps < a.npass; ++ps) {
+    const int colour = a.npass > 1 ? a.colours[ps] : a.colour;
+    px = colour & 1;
+    py = colour >> 1;
+    perm = a.order + (size_t)colour * npairs * nay;
+    work = a.work + ps;
+    pdU = a.partial_dU + (size_t)ps * a.dU_stride;
+    pass_no = a.pass + ps;
     int it0 = blockIdx.x * wpb + wib;
-    int it1 = 2 * W - 1 - it0;  // a heavy first item is paired with a light second one
-    int it2 = __shfl_sync(FULL_MASK, ticket(), 0);
-    int acy1 = load_perm(it1);
-    ItemMeta m0 = load_counts(it0, load_perm(it0));
+    const int acy0 = load_perm(it0);  // the order does not change during a sweep: fetched before the barrier
+    if (ps > 0) cooperative_groups::this_grid().sync();  // the cells of the previous colour are written
+    ItemMeta m0 = load_counts(it0, acy0);
 
     while (it0 < a.nitems) {
-        // issue the prefetches of the following items (consumed at the bottom of this iteration)
-        const int tick = ticket();
-        const int acy2 = load_perm(it2);
-        const ItemMeta m1 = load_counts(it1, acy1);
+        const int tick = ticket();  // in flight during the staging of this item
+        int it1 = 0, acy1 = -1;
+        ItemMeta m1;
+        bool have_it1 = false, have_m1 = false;
 
         const bool has_cell = m0.acy >= 0;
         const int acx = a.pair_lo + it0 % a.pair_n;
@@ -347,23 +368,32 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
             }
             cp_async_wait_all();
             __syncwarp();
+            if (!have_it1) {  // the ticket has arrived by now; the sorted cell of the next item travels during the rounds
+                it1 = __shfl_sync(FULL_MASK, tick, 0);
+                acy1 = load_perm(it1);
+                have_it1 = true;
+            }
             // to cell-local coordinates, in place
             for (int k = sl; k < Ms + n_own; k += G) cand[k] = to_local(cand[k], x_lo, y_lo, g, hLx, hLy);
             __syncwarp();
 
             bool dirty = false;
             Philox4 batch = {0u, 0u, 0u, 0u};
+            double batchE = 0.0;
 
             // ---- K2: displacement rounds (MC.cpp:96-123); one trial per group per round ----
             {
                 const int T = warp_max_int(n_disp);
                 for (int t = 0; t < T; ++t) {
-                    if ((t & (G - 1)) == 0)  // sub-lane s draws the words of trial t + s of its cell's stream
+                    if ((t & (G - 1)) == 0) {  // sub-lane s draws the words of trial t + s of its cell's stream
                         batch = philox4x32_10(cell_gid, MC2D_TAG_DISP | (uint32_t)(t + sl), a.sweep_lo, a.sweep_hi,
                                               a.seed_lo, a.seed_hi);
+                        batchE = mc2d_exp_variate(batch.w);  // -ln u of that trial: off the critical path
+                    }
                     const int src = src_base + (t & (G - 1));
                     const uint32_t rx = __shfl_sync(FULL_MASK, batch.x, src), ry = __shfl_sync(FULL_MASK, batch.y, src);
-                    const uint32_t rz = __shfl_sync(FULL_MASK, batch.z, src), rw = __shfl_sync(FULL_MASK, batch.w, src);
+                    const uint32_t rz = __shfl_sync(FULL_MASK, batch.z, src);
+                    const double Et = __shfl_sync(FULL_MASK, batchE, src);
                     const bool act = t < n_disp;
                     const int i = act ? (int)__umulhi(rx, (uint32_t)n_own) : 0;
                     const double2 uo = act ? own[i] : make_double2(0.0, 0.0);
@@ -386,9 +416,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                         }
                         dE = escale * group_sum<G>(acc);
                     }
-                    bool accept = inside && (dE <= 0.0);
-                    if (__any_sync(FULL_MASK, inside && dE > 0.0))
-                        accept = accept || (inside && mc2d_u01(rw) < exp(-a.beta * dE));  // MC.cpp:110-115
+                    const bool accept = inside && (a.beta * dE < Et);  // MC.cpp:110-115, log form (sweep_kernel.cuh)
                     if (accept && sl == 0) own[i] = un;
                     if (sl == 0) {
                         c_att[0] += act;
@@ -400,7 +428,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                         unsigned long long slot = atomicAdd(a.trace_n, 1ull);
                         if ((long long)slot < a.trace_cap) {
                             mc2d_trial tr;
-                            tr.pass = a.pass; tr.cell = (int)cell_gid; tr.seq = t; tr.kind = 0;
+                            tr.pass = pass_no; tr.cell = (int)cell_gid; tr.seq = t; tr.kind = 0;
                             tr.accepted = accept ? 1 : 0; tr.reserved = inside ? 1 : 0;
                             double ox_ = x_lo + uo.x, oy_ = y_lo + uo.y, nx_ = x_lo + un.x, ny_ = y_lo + un.y;
                             if (ox_ >= g.Lx) ox_ -= g.Lx; if (oy_ >= g.Ly) oy_ -= g.Ly;
@@ -414,16 +442,24 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                 }
             }
 
+            if (!have_m1) {  // the counts of the next item travel during the GC rounds and the write-back
+                m1 = load_counts(it1, acy1);
+                have_m1 = true;
+            }
+
             // ---- K3: grand-canonical rounds (MC.cpp:189-249); insertion and deletion share one probe loop ----
             {
                 const int T = warp_max_int(n_gc);
                 for (int t = 0; t < T; ++t) {
-                    if ((t & (G - 1)) == 0)
+                    if ((t & (G - 1)) == 0) {
                         batch = philox4x32_10(cell_gid, MC2D_TAG_GC | (uint32_t)(t + sl), a.sweep_lo, a.sweep_hi,
                                               a.seed_lo, a.seed_hi);
+                        batchE = mc2d_exp_variate(batch.w);
+                    }
                     const int src = src_base + (t & (G - 1));
                     const uint32_t rx = __shfl_sync(FULL_MASK, batch.x, src), ry = __shfl_sync(FULL_MASK, batch.y, src);
-                    const uint32_t rz = __shfl_sync(FULL_MASK, batch.z, src), rw = __shfl_sync(FULL_MASK, batch.w, src);
+                    const uint32_t rz = __shfl_sync(FULL_MASK, batch.z, src);
+                    const double Et = __shfl_sync(FULL_MASK, batchE, src);
                     const bool act = t < n_gc;
                     const double sel = mc2d_u01(rx);
                     const int kind = !act ? 0 : (sel < a.p_ins ? 1 : (sel < a.p_ins + a.p_del ? 2 : 0));
@@ -449,10 +485,9 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                         acc = escale * group_sum<G>(acc);
                         dE = (kind == 2) ? -acc : acc;  // MC.cpp:200,225
                     }
-                    // MC.cpp:201 and :226, per-cell form
-                    const double pref = (kind == 1) ? a.zA / (double)(n_own + 1) : (double)n_own / a.zA;
-                    const double av = pref * exp(-a.beta * dE);
-                    const bool accept = evaluate && ((av >= 1.0) || (mc2d_u01(rw) < av));
+                    // MC.cpp:201 and :226, per-cell form, in log form: ln of z A / (n + 1) or of n / (z A)
+                    const double ln_pref = (kind == 1) ? ln_zA - lntab[n_own + 1] : lntab[n_own] - ln_zA;
+                    const bool accept = evaluate && (a.beta * dE - ln_pref < Et);
                     if (sl == 0) {
                         if (accept && kind == 1) {
                             own[n_own] = pt;
@@ -475,7 +510,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                         unsigned long long slot = atomicAdd(a.trace_n, 1ull);
                         if ((long long)slot < a.trace_cap) {
                             mc2d_trial tr;
-                            tr.pass = a.pass; tr.cell = (int)cell_gid; tr.seq = n_disp + t; tr.kind = kind;
+                            tr.pass = pass_no; tr.cell = (int)cell_gid; tr.seq = n_disp + t; tr.kind = kind;
                             tr.accepted = accept ? 1 : 0; tr.reserved = evaluate ? 1 : 0;
                             const double2 o_ = (kind == 2 && evaluate) ? old : make_double2(0.0, 0.0);
                             const double2 p_ = (kind == 1) ? pt : make_double2(0.0, 0.0);
@@ -509,15 +544,13 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         } while (__any_sync(FULL_MASK, pending));
         // energy change of this item, summed in lane order; the slot is private to the item
         const double dU_w = warp_sum(dU_total);
-        if (lane == 0) a.partial_dU[(it0 / a.pair_n) * npairs + acx] += dU_w;  // the item's slot in the full list
+        if (lane == 0) pdU[(it0 / a.pair_n) * npairs + acx] += dU_w;  // the item's slot in the full list
         __syncwarp();  // the next item's staging reuses this warp's shared memory
 
         it0 = it1;
-        it1 = it2;
-        it2 = __shfl_sync(FULL_MASK, tick, 0);
         m0 = m1;
-        acy1 = acy2;
     }
+  }
 
     // ---- epilogue: move counters ----
     unsigned int cw[7] = {c_att[0], c_att[1], c_att[2], c_acc[0], c_acc[1], c_acc[2], c_ovf};
