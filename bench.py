@@ -298,6 +298,30 @@ def main():
     # half-shell reduction: every undirected in-cutoff pair is evaluated once
     pair_rate = allsum(pair_evals) / (allmax(energy_ms) * 1e-3) if energy_ms > 0 else None
 
+    # ---- the same step with two displacement trials per particle and cell visit (HOOMD's nselect = 2) -----------
+    # A colour pass has a fixed cost (launch, index chain, staging of the 9 cells) that 1 trial per particle pays
+    # in full; more trials per visit are a legal schedule of the same ensemble (detailed balance holds per trial).
+    # Reported next to `value`, which stays at the reference's sweep: N displacement trials + the GC draws.
+    ctx.reset_counters()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(max(3, args.steps // 2))]
+    for _ in range(2):
+        ctx.run_sweeps(S, disp_per_particle=2, gc_per_cell=1)
+    ctx.reset_counters()
+    barrier()
+    for a2, b2 in ev2:
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        a2.record(stream)
+        st2 = ctx.run_sweeps(S, disp_per_particle=2, gc_per_cell=1)
+        ctx.total_energy_virial(resync=True, allreduce=world > 1)
+        b2.record(stream)
+    barrier()
+    ms2 = allmax(sum(a2.elapsed_time(b2) for a2, b2 in ev2))
+    nselect2 = {"value": allsum(sum(st2["attempted"])) / (ms2 * 1e-3), "unit": "moves/s", "steps": len(ev2),
+                "ms_per_step": ms2 / len(ev2),
+                "what": "same step with disp_per_particle = 2 (two displacement trials per particle per cell visit)"}
+    ctx.run_sweeps(S, disp_per_particle=1, gc_per_cell=1)
+
     # ---- roofline of the dominant kernel (k_sweep), CUDA events around every launch ----------
     ctx.set_kernel_timing(True)
     ctx.reset_counters()
@@ -392,6 +416,8 @@ def main():
                        "potential": "LennardJones", "rcut": RCUT, "T": T_BENCH, "rho": RHO,
                        "activity": Z_LJ_T1_RHO05, "delta": DELTA, "ensemble": "GCMC",
                        "sweeps_per_step": S, "step": "%d GCMC sweeps + 1 energy/virial reduction" % S,
+                       "sweep": "4 colour passes; per cell visit 1 displacement trial per particle + 1 GC draw "
+                                "(the reference's step: N displacement trials + GC, MC.cpp:36-52)",
                        "grid": [info.nx, info.ny], "cell_capacity": info.cell_capacity,
                        "decomposition": "1-D slabs in x, %d rank(s)" % world,
                        "halo": {0: "none (single rank)", 1: "ncclSend/ncclRecv of whole slot columns",
@@ -401,7 +427,7 @@ def main():
                              "event pairs); slot arrays are %.0f MB per buffer"
                              % (info.ncol * info.ny * info.cell_capacity * 16 / 1e6)},
             "pair_evals_per_s": pair_rate, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "nselect2": nselect2,
             "acceptance": {"displacement": st["accepted"][0] / max(st["attempted"][0], 1),
                            "insertion": st["accepted"][1] / max(st["attempted"][1], 1),
                            "deletion": st["accepted"][2] / max(st["attempted"][2], 1)},
