@@ -1480,7 +1480,10 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
         // single rank / no overlap: the four passes of a sweep go out as ONE cooperative launch (grid barrier between
         // colours); MC2D_SWEEP_FUSE=0 launches them one by one
         const bool fuse = persistent && !overlap && !g.ghost && ctx->fuse_passes;
-        for (int p = 0; p < (fuse ? 1 : 4); ++p) {
+        // slab mode: the same single launch, with the halo exchange inside the kernel (boundary items wait on the
+        // neighbour's flag word, push their cells into its ghost column, the last one signals)
+        const bool fuse_halo = overlap && ctx->fuse_passes && (nitems / npairs) <= ctx->num_sms * wpb;
+        for (int p = 0; p < ((fuse || fuse_halo) ? 1 : 4); ++p) {
             SweepArgs a;
             a.pos = ctx->pos[ctx->cur];
             a.cnt = ctx->cnt[ctx->cur];
@@ -1490,9 +1493,18 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             a.nitems = nitems;
             a.pair_lo = 0;
             a.pair_n = npairs;
-            a.npass = fuse ? 4 : 1;
+            a.npass = (fuse || fuse_halo) ? 4 : 1;
             for (int q = 0; q < 4; ++q) a.colours[q] = order[q];
             a.dU_stride = nblocks;
+            a.halo_fused = 0;
+            a.myflag = nullptr;
+            a.seq_base = 0;
+            for (int q = 0; q < 2; ++q) {
+                a.hpos[q] = nullptr;
+                a.hcnt[q] = nullptr;
+                a.hids[q] = nullptr;
+                a.hflag[q] = nullptr;
+            }
             a.g = g;
             a.pp = ctx->pp;
             a.r2cut = ctx->r2cut;
@@ -1534,6 +1546,27 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
                 return rc;
             };
             int rc = MC2D_OK;
+            if (fuse_halo) {
+                if ((rc = join())) return rc;  // the re-bin's boundary part and its push ran on the other stream
+                const size_t colp = (size_t)g.ny * g.K, colc = (size_t)g.ny;
+                const int ghost_col[2] = {g.ghost + g.ncol, 0};  // my first column lands in the LEFT neighbour's RIGHT ghost
+                for (int side = 0; side < 2; ++side) {
+                    char *pb = ctx->peer_base[side];
+                    a.hpos[side] = reinterpret_cast<double2 *>(pb + ctx->off_pos[ctx->cur]) + (size_t)ghost_col[side] * colp;
+                    a.hcnt[side] = reinterpret_cast<int *>(pb + ctx->off_cnt[ctx->cur]) + (size_t)ghost_col[side] * colc;
+                    a.hids[side] = ctx->use_ids ? reinterpret_cast<int *>(pb + ctx->off_ids[ctx->cur]) + (size_t)ghost_col[side] * colp
+                                                : nullptr;
+                    a.hflag[side] = reinterpret_cast<unsigned long long *>(pb) + (side == 0 ? 1 : 0);
+                }
+                a.myflag = reinterpret_cast<unsigned long long *>(ctx->arena);
+                a.seq_base = ctx->halo_seq;
+                a.halo_fused = 1;
+                ctx->halo_seq += 4;  // one sync point per colour pass, signalled from inside the kernel
+                if ((rc = ktime_begin(ctx, 3))) return rc;
+                if ((rc = launch_items(a, sa, 0))) return rc;
+                if ((rc = ktime_end(ctx))) return rc;
+                continue;
+            }
             if (overlap) {
                 const bool left = (order[p] & 1) == 0;  // even columns active: the first owned column changes
                 const int items_per_pair = nitems / npairs;

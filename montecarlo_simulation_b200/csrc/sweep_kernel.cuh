@@ -31,6 +31,14 @@ struct SweepArgs {
     int npass;            // k_sweep_p: colour passes done by this launch: 1, or 4 with a grid barrier in between
     int colours[4];       //            their colours (npass > 1); pass p uses work[p] and partial_dU + p * dU_stride
     int dU_stride;
+    // k_sweep_p, slab mode with all passes in one launch: the halo is part of the kernel (sweep_kernel_p.cuh)
+    int halo_fused;
+    double2 *hpos[2];                // [0] left neighbour's right-ghost column, [1] right neighbour's left-ghost column
+    int *hcnt[2];
+    int *hids[2];
+    unsigned long long *hflag[2];    // the neighbours' flag words this rank signals
+    unsigned long long *myflag;      // [0] from left, [1] from right, [3] finished boundary items of the pass
+    unsigned long long seq_base;     // sync sequence number reached before this launch
     Grid g;
     PairParams pp;
     double r2cut, beta, zA, delta;

@@ -16,6 +16,14 @@
 //  * The index chain of an item (work ticket -> sorted cell -> 9 cell counts) is prefetched into
 //    registers while the previous items run: staging starts with the position loads.
 //
+// Slab mode (halo_fused): the halo exchange is part of this kernel.  The items of the boundary column pair of a
+// pass come first in the item list; their warps wait for the neighbour's flag word (the ghost column they read is
+// complete), read that column past the L1, and after the write-back store their cells straight into the
+// neighbour's ghost column (peer memory over NVLink).  The warp that finishes the last boundary item of the pass
+// fences and stores the next sync sequence number into both neighbours' flag words.  The interior items never
+// touch a ghost, so the NVLink traffic and the neighbour's latency hide behind them; the grid barrier between
+// colours is local.  (Protocol and hazards: k_halo_sync in group_kernels.cuh.)
+//
 // The energy change of a pass is accumulated per ITEM (fixed composition, fixed order inside the
 // warp), so the running energy stays reproducible although items are scheduled dynamically.
 #pragma once
@@ -157,6 +165,11 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+// L2-only variant: for cells a neighbour GPU writes while this kernel runs (the L1 of this SM may hold an older copy)
+__device__ __forceinline__ void cp_async16_cg(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
@@ -263,24 +276,45 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         if (lane == 0) v = W + atomicAdd(work, 1);
         return v;
     };
+    const int ipp = (nay + GPW - 1) / GPW;  // items per column pair
+    int bpair = 0;                          // slab mode: the boundary pair of this pass, its items are 0 .. ipp-1
+    auto split = [&](int item, int &p, int &r) {  // item -> column pair, rank inside the pair
+        if (a.halo_fused) {
+            if (item < ipp) {
+                p = bpair;
+                r = item;
+            } else {
+                const int idx = item - ipp, m = npairs - 1, q = idx % m;
+                r = idx / m;
+                p = q + (q >= bpair ? 1 : 0);
+            }
+        } else {
+            p = a.pair_lo + item % a.pair_n;
+            r = item / a.pair_n;
+        }
+    };
     auto load_perm = [&](int item) {  // -> acy of this group's cell in `item`, or -1
-        const int p = a.pair_lo + item % a.pair_n, j = (item / a.pair_n) * GPW + gi;
+        int p, r;
+        split(item, p, r);
+        const int j = r * GPW + gi;
         return (item < a.nitems && j < nay) ? perm[(size_t)p * nay + j] : -1;
     };
-    auto load_counts = [&](int item, int acy) {
+    auto load_counts = [&](int item, int acy, bool past_l1) {
         ItemMeta m;
         m.acy = acy;
         m.n_own = 0;
         m.c_lo = m.c_hi = 0;
         if (acy >= 0) {
-            int col3[3], row3[3];
-            nbr_rows_cols(g, g.ghost + 2 * (a.pair_lo + item % a.pair_n) + px, 2 * acy + py, col3, row3);
+            int col3[3], row3[3], p, r;
+            split(item, p, r);
+            nbr_rows_cols(g, g.ghost + 2 * p + px, 2 * acy + py, col3, row3);
             m.n_own = a.cnt[col3[1] + row3[1]];
             if (POT != POT_IDEAL) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const int o = q + (q >= 4);
-                    const uint32_t n = (uint32_t)a.cnt[col3[o / 3] + row3[o % 3]];
+                    const int *pc = &a.cnt[col3[o / 3] + row3[o % 3]];
+                    const uint32_t n = (uint32_t)(past_l1 ? __ldcg(pc) : *pc);
                     if (q < 4) m.c_lo |= n << (8 * q);
                     else m.c_hi |= n << (8 * (q - 4));
                 }
@@ -296,10 +330,20 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
     work = a.work + ps;
     pdU = a.partial_dU + (size_t)ps * a.dU_stride;
     pass_no = a.pass + ps;
+    bpair = (px == 0) ? 0 : npairs - 1;   // even columns active: the first owned column is the one at the slab edge
+    const int hside = (px == 0) ? 0 : 1;  // ... it reads the left ghost and is pushed to the left neighbour
     int it0 = blockIdx.x * wpb + wib;
     const int acy0 = load_perm(it0);  // the order does not change during a sweep: fetched before the barrier
     if (ps > 0) cooperative_groups::this_grid().sync();  // the cells of the previous colour are written
-    ItemMeta m0 = load_counts(it0, acy0);
+    if (a.halo_fused && it0 < ipp) {  // boundary item: wait until the neighbour has completed the ghost column it reads
+        if (lane == 0) {
+            const volatile unsigned long long *f = a.myflag;
+            while (f[hside] < a.seq_base + (unsigned long long)ps) __nanosleep(32);
+        }
+        __syncwarp();
+        __threadfence();
+    }
+    ItemMeta m0 = load_counts(it0, acy0, a.halo_fused && it0 < ipp);
 
     while (it0 < a.nitems) {
         const int tick = ticket();  // in flight during the staging of this item
@@ -308,7 +352,9 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         bool have_it1 = false, have_m1 = false;
 
         const bool has_cell = m0.acy >= 0;
-        const int acx = a.pair_lo + it0 % a.pair_n;
+        const bool bitem = a.halo_fused && it0 < ipp;  // item of the slab-edge column pair (warp uniform)
+        int acx, it0_rank;
+        split(it0, acx, it0_rank);
         const int lcx = g.ghost + 2 * acx + px, cy = 2 * max(m0.acy, 0) + py, gcx = g.col0 + 2 * acx + px;
         const int cell = lcx * g.ny + cy;
         const uint32_t cell_gid = (uint32_t)(gcx * g.ny + cy);
@@ -348,6 +394,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                     cp_async16(&own[s], &a.pos[(size_t)cell * K + s]);
                     if (a.ids) own_id[s] = a.ids[(size_t)cell * K + s];
                 }
+                // (own cells are written by this GPU only; the neighbours' cells of a boundary item include the ghost)
                 if (Ms > 0) {  // lane sl copies neighbour cells sl, sl + G, ...
                     int col3[3], row3[3];
                     nbr_rows_cols(g, lcx, cy, col3, row3);
@@ -362,7 +409,10 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                         const int cb = oc == 0 ? col3[0] : (oc == 1 ? col3[1] : col3[2]);
                         const int rb = orow == 0 ? row3[0] : (orow == 1 ? row3[1] : row3[2]);
                         const double2 *src = a.pos + (size_t)(cb + rb) * K;
-                        for (int s = 0; s < n; ++s) cp_async16(&cand[pre + s], &src[s]);
+                        if (bitem)
+                            for (int s = 0; s < n; ++s) cp_async16_cg(&cand[pre + s], &src[s]);
+                        else
+                            for (int s = 0; s < n; ++s) cp_async16(&cand[pre + s], &src[s]);
                     }
                 }
             }
@@ -443,7 +493,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
             }
 
             if (!have_m1) {  // the counts of the next item travel during the GC rounds and the write-back
-                m1 = load_counts(it1, acy1);
+                m1 = load_counts(it1, acy1, false);  // tickets start behind the boundary items
                 have_m1 = true;
             }
 
@@ -535,8 +585,15 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                     if (y >= g.Ly) y -= g.Ly; else if (y < 0.0) y += g.Ly;
                     a.pos[(size_t)cell * K + s] = make_double2(x, y);
                     if (a.ids) a.ids[(size_t)cell * K + s] = own_id[s];
+                    if (bitem) {  // ... and into the neighbour's ghost column
+                        a.hpos[hside][(size_t)cy * K + s] = make_double2(x, y);
+                        if (a.ids) a.hids[hside][(size_t)cy * K + s] = own_id[s];
+                    }
                 }
-                if (sl == 0) a.cnt[cell] = n_own;
+                if (sl == 0) {
+                    a.cnt[cell] = n_own;
+                    if (bitem) a.hcnt[hside][cy] = n_own;
+                }
             }
             __syncwarp();  // the next batch / item reuses this warp's slots
             start = warp_max_int(work ? incl : start);
@@ -544,7 +601,22 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         } while (__any_sync(FULL_MASK, pending));
         // energy change of this item, summed in lane order; the slot is private to the item
         const double dU_w = warp_sum(dU_total);
-        if (lane == 0) pdU[(it0 / a.pair_n) * npairs + acx] += dU_w;  // the item's slot in the full list
+        if (lane == 0) pdU[it0_rank * npairs + acx] += dU_w;  // the item's slot in the full list
+        if (bitem) {  // one more boundary item done; the last one signals both neighbours
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned long long done = atomicAdd(&a.myflag[3], 1ull);
+                if (done == (unsigned long long)(ipp - 1)) {
+                    __threadfence_system();
+                    a.myflag[3] = 0;  // the next pass starts counting after the grid barrier
+                    const unsigned long long seq = a.seq_base + (unsigned long long)ps + 1ull;
+                    *(volatile unsigned long long *)a.hflag[0] = seq;
+                    *(volatile unsigned long long *)a.hflag[1] = seq;
+                    __threadfence_system();
+                }
+            }
+        }
         __syncwarp();  // the next item's staging reuses this warp's shared memory
 
         it0 = it1;
