@@ -278,35 +278,45 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
     };
     const int ipp = (nay + GPW - 1) / GPW;  // items per column pair
     int bpair = 0;                          // slab mode: the boundary pair of this pass, its items are 0 .. ipp-1
-    auto split = [&](int item, int &p, int &r) {  // item -> column pair, rank inside the pair
+    // item -> column pair, rank inside the pair; the division is a multiplication by the reciprocal + one fix-up
+    const unsigned div_n = (unsigned)(a.halo_fused ? npairs - 1 : a.pair_n), div_inv = 0xFFFFFFFFu / div_n;
+    auto divmod = [&](unsigned x, unsigned &q, unsigned &rem) {
+        q = __umulhi(x, div_inv);  // floor(x / n) or one less
+        rem = x - q * div_n;
+        if (rem >= div_n) {
+            ++q;
+            rem -= div_n;
+        }
+    };
+    auto split = [&](int item, int &p, int &r) {
+        unsigned q, rem;
         if (a.halo_fused) {
             if (item < ipp) {
                 p = bpair;
                 r = item;
             } else {
-                const int idx = item - ipp, m = npairs - 1, q = idx % m;
-                r = idx / m;
-                p = q + (q >= bpair ? 1 : 0);
+                divmod((unsigned)(item - ipp), q, rem);
+                r = (int)q;
+                p = (int)rem + ((int)rem >= bpair ? 1 : 0);
             }
         } else {
-            p = a.pair_lo + item % a.pair_n;
-            r = item / a.pair_n;
+            divmod((unsigned)item, q, rem);
+            p = a.pair_lo + (int)rem;
+            r = (int)q;
         }
     };
-    auto load_perm = [&](int item) {  // -> acy of this group's cell in `item`, or -1
-        int p, r;
+    auto load_perm = [&](int item, int &p, int &r) {  // -> acy of this group's cell (or -1); the item's pair and rank
         split(item, p, r);
         const int j = r * GPW + gi;
         return (item < a.nitems && j < nay) ? perm[(size_t)p * nay + j] : -1;
     };
-    auto load_counts = [&](int item, int acy, bool past_l1) {
+    auto load_counts = [&](int p, int acy, bool past_l1) {
         ItemMeta m;
         m.acy = acy;
         m.n_own = 0;
         m.c_lo = m.c_hi = 0;
         if (acy >= 0) {
-            int col3[3], row3[3], p, r;
-            split(item, p, r);
+            int col3[3], row3[3];
             nbr_rows_cols(g, g.ghost + 2 * p + px, 2 * acy + py, col3, row3);
             m.n_own = a.cnt[col3[1] + row3[1]];
             if (POT != POT_IDEAL) {
@@ -333,7 +343,8 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
     bpair = (px == 0) ? 0 : npairs - 1;   // even columns active: the first owned column is the one at the slab edge
     const int hside = (px == 0) ? 0 : 1;  // ... it reads the left ghost and is pushed to the left neighbour
     int it0 = blockIdx.x * wpb + wib;
-    const int acy0 = load_perm(it0);  // the order does not change during a sweep: fetched before the barrier
+    int acx = 0, it0_rank = 0;  // column pair of the current item and its rank inside the pair
+    const int acy0 = load_perm(it0, acx, it0_rank);  // the order does not change during a sweep: fetched before the barrier
     if (ps > 0) cooperative_groups::this_grid().sync();  // the cells of the previous colour are written
     if (a.halo_fused && it0 < ipp) {  // boundary item: wait until the neighbour has completed the ghost column it reads
         if (lane == 0) {
@@ -343,18 +354,16 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         __syncwarp();
         __threadfence();
     }
-    ItemMeta m0 = load_counts(it0, acy0, a.halo_fused && it0 < ipp);
+    ItemMeta m0 = load_counts(acx, acy0, a.halo_fused && it0 < ipp);
 
     while (it0 < a.nitems) {
         const int tick = ticket();  // in flight during the staging of this item
-        int it1 = 0, acy1 = -1;
+        int it1 = 0, acy1 = -1, acx1 = 0, rank1 = 0;
         ItemMeta m1;
         bool have_it1 = false, have_m1 = false;
 
         const bool has_cell = m0.acy >= 0;
         const bool bitem = a.halo_fused && it0 < ipp;  // item of the slab-edge column pair (warp uniform)
-        int acx, it0_rank;
-        split(it0, acx, it0_rank);
         const int lcx = g.ghost + 2 * acx + px, cy = 2 * max(m0.acy, 0) + py, gcx = g.col0 + 2 * acx + px;
         const int cell = lcx * g.ny + cy;
         const uint32_t cell_gid = (uint32_t)(gcx * g.ny + cy);
@@ -420,7 +429,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
             __syncwarp();
             if (!have_it1) {  // the ticket has arrived by now; the sorted cell of the next item travels during the rounds
                 it1 = __shfl_sync(FULL_MASK, tick, 0);
-                acy1 = load_perm(it1);
+                acy1 = load_perm(it1, acx1, rank1);
                 have_it1 = true;
             }
             // to cell-local coordinates, in place
@@ -493,7 +502,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
             }
 
             if (!have_m1) {  // the counts of the next item travel during the GC rounds and the write-back
-                m1 = load_counts(it1, acy1, false);  // tickets start behind the boundary items
+                m1 = load_counts(acx1, acy1, false);  // tickets start behind the boundary items
                 have_m1 = true;
             }
 
@@ -620,6 +629,8 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         __syncwarp();  // the next item's staging reuses this warp's shared memory
 
         it0 = it1;
+        acx = acx1;
+        it0_rank = rank1;
         m0 = m1;
     }
   }
