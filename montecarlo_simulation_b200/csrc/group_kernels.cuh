@@ -313,8 +313,8 @@ __global__ void __launch_bounds__(256) k_halo_sync(HaloArgs h) {
 // as cell-local coordinates.  Half shell: a cell pairs its own particles (j > i) and those of its 4
 // forward neighbours (0,+1), (+1,-1), (+1,0), (+1,+1), so every unordered pair is evaluated once; in a
 // slab the last owned column pairs with the right ghost column and the first one leaves its left
-// pairs to the left rank.  LJ / WCA accumulate a = sum r^-12 and b = sum r^-6 (one reciprocal with one
-// Newton step per pair): U = 4 (a - b) [+ 1 per WCA pair], W = 48 a - 24 b.
+// pairs to the left rank.  LJ / WCA accumulate a = sum r^-12 and b = sum r^-6 (one hardware reciprocal + Newton
+// steps per pair, rcp_newton1): U = 4 (a - b) [+ 1 per WCA pair], W = 48 a - 24 b.
 // Items whose candidates do not fit in the group's shared memory raise err[3]; the host then repeats
 // the reduction with k_energy_virial_g.
 // ------------------------------------------------------------------------------------------------

@@ -174,14 +174,19 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// 1/x from the hardware seed (rcp.approx.ftz.f64, relative error <= 2^-23) and ONE Newton step:
-// relative error <= 2^-46 = 1.4e-14, four orders below the 1e-10 bound on per-trial dE
-// (tests/test_gpu_parity.py::test_per_trial_dE_matches_oracle); the parity hooks K4/K6 keep the
-// IEEE division of the reference.
+// 1/x from the hardware seed (rcp.approx.ftz.f64, ~20 good bits) and MC2D_SWEEPP_NEWTON Newton steps.  One step
+// leaves ~1e-12 per reciprocal (worst per-trial dE error measured against the oracle: 7e-12 of max(1, |dE|),
+// tools/check_dE_accuracy.py); two steps reach the last bit (worst 1e-15) and cost two more DFMA per pair.
+// The parity hooks K4/K6 keep the IEEE division of the reference.
+#ifndef MC2D_SWEEPP_NEWTON
+#define MC2D_SWEEPP_NEWTON 2
+#endif
 __device__ __forceinline__ double rcp_newton1(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    return fma(r, fma(-x, r, 1.0), r);
+#pragma unroll
+    for (int it = 0; it < MC2D_SWEEPP_NEWTON; ++it) r = fma(r, fma(-x, r, 1.0), r);
+    return r;
 }
 
 // Empty candidate slots hold this point: its distance to anything in a cell is ~1e150, beyond every
