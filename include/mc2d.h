@@ -214,6 +214,19 @@ int mc2d_allreduce_stats(mc2d_ctx *ctx, mc2d_stats *inout);
 int mc2d_rescale_try(mc2d_ctx *ctx, double Lx_new, double Ly_new, double *U_new, double *W_new);
 int mc2d_rescale_finish(mc2d_ctx *ctx, int accept);
 
+/* -- single-particle probes on the resident configuration (Gibbs-ensemble particle exchange,
+ *    GibbsMC.cpp:340-394; also Widom insertion) ---------------------------------------------------
+ * mc2d_probe_point:    dU = energy of a test particle at (x, y) against the configuration
+ *                      (getNeighbors2 + computeLocalEnergy, exact reference arithmetic).
+ * mc2d_probe_particle: the index-th particle in the order mc2d_download would return them
+ *                      (0 <= index < N): its position and dU = MINUS its energy with its neighbours.
+ * mc2d_apply_probe:    what != 0 carries out the probed insertion (what = 1) or deletion (what = 2):
+ *                      positions, counts and the running energy are updated; 0 forgets the probe.
+ * Single-rank contexts; MC2D_ERR_CELL_OVERFLOW if the target cell of an insertion has no free slot. */
+int mc2d_probe_point(mc2d_ctx *ctx, double x, double y, double *dU);
+int mc2d_probe_particle(mc2d_ctx *ctx, long long index, double *x, double *y, double *dU);
+int mc2d_apply_probe(mc2d_ctx *ctx, int what);
+
 /* -- introspection for benchmarks ------------------------------------------------------------ */
 typedef struct {
     int nx, ny;            /* checkerboard grid */

@@ -80,7 +80,7 @@ EXPORTS = [
     "mc2d_calc_cell_ids", "mc2d_calc_neighbor_counts", "mc2d_calc_point_energies", "mc2d_run_sweep_traced",
     "mc2d_comm_unique_id", "mc2d_comm_init", "mc2d_allreduce_stats", "mc2d_get_info", "mc2d_get_stream",
     "mc2d_synchronize", "mc2d_set_kernel_timing", "mc2d_calc_neighbor_list", "mc2d_calc_energy_virial_bruteforce",
-    "mc2d_rescale_try", "mc2d_rescale_finish",
+    "mc2d_rescale_try", "mc2d_rescale_finish", "mc2d_probe_point", "mc2d_probe_particle", "mc2d_apply_probe",
 ]
 
 _lib = None
@@ -133,6 +133,9 @@ def load_library() -> C.CDLL:
     L.mc2d_calc_energy_virial_bruteforce.argtypes = [vp, vp, ll, dp, dp]
     L.mc2d_rescale_try.argtypes = [vp, d, d, dp, dp]
     L.mc2d_rescale_finish.argtypes = [vp, i]
+    L.mc2d_probe_point.argtypes = [vp, d, d, dp]
+    L.mc2d_probe_particle.argtypes = [vp, ll, dp, dp, dp]
+    L.mc2d_apply_probe.argtypes = [vp, i]
     _lib = L
     return L
 
@@ -415,6 +418,21 @@ class Context:
 
     def rescale_finish(self, accept: bool):
         self._check(self.L.mc2d_rescale_finish(self.h, int(bool(accept))))
+
+    def probe_point(self, x, y):
+        """energy of a test particle at (x, y) against the resident configuration"""
+        dU = C.c_double()
+        self._check(self.L.mc2d_probe_point(self.h, x, y, C.byref(dU)))
+        return dU.value
+
+    def probe_particle(self, index):
+        """(x, y, dU) of the index-th particle in download order; dU = minus its energy with its neighbours"""
+        x, y, dU = C.c_double(), C.c_double(), C.c_double()
+        self._check(self.L.mc2d_probe_particle(self.h, index, C.byref(x), C.byref(y), C.byref(dU)))
+        return x.value, y.value, dU.value
+
+    def apply_probe(self, what: int):
+        self._check(self.L.mc2d_apply_probe(self.h, what))
 
     def set_kernel_timing(self, on: bool):
         self._check(self.L.mc2d_set_kernel_timing(self.h, int(on)))

@@ -447,3 +447,84 @@ __global__ void __launch_bounds__(256) k_scale_slots(const double2 *pos_o, const
         if (ids_n) ids_n[i] = ids_o[i];
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Single-particle probes on the slot layout (Gibbs-ensemble particle exchange, GibbsMC.cpp:340-394).
+// One warp.  mode 0: energy of a test particle at pt (getNeighbors2, cell_list.cpp:72-101); mode 1: the
+// index-th particle in cell-major order (offsets = exclusive scan of the owned cells' counts), its energy with
+// its neighbours, negated (cell_list.cpp:43-70).  Exact reference distance arithmetic, IEEE division.
+// out: [0] dU, [1] x, [2] y; sel: [0] stored cell, [1] slot.
+// ------------------------------------------------------------------------------------------------
+template <int POT>
+__global__ void __launch_bounds__(32) k_probe_slots(const double2 *pos, const int *cnt, Grid g, PairParams pp,
+                                                    double r2cut, int mode, double2 pt, long long index,
+                                                    const int *offsets, double *out, int *sel) {
+    const int lane = threadIdx.x;
+    const int ncell = g.ncol * g.ny, cell0 = g.ghost * g.ny;
+    int cell = -1, slot = -1;
+    if (mode == 1) {
+        int lo = 0, hi = ncell - 1;  // last owned cell whose offset is <= index
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((long long)offsets[mid] <= index) lo = mid; else hi = mid - 1;
+        }
+        cell = cell0 + lo;
+        slot = (int)(index - offsets[lo]);
+        pt = pos[(size_t)cell * g.K + slot];
+    } else {
+        int gcx, cy;
+        sweep_cell_of(g, pt.x, pt.y, gcx, cy);
+        cell = (gcx - g.col0 + g.ghost) * g.ny + cy;
+    }
+    const int lcx = cell / g.ny, cy = cell - lcx * g.ny;
+    const double hLx = 0.5 * g.Lx, hLy = 0.5 * g.Ly;
+    double acc = 0.0;
+    for (int c = 0; c < 9; ++c) {
+        const int ddx = c / 3 - 1, ddy = c % 3 - 1;
+        if ((g.nx == 2 && ddx < 0) || (g.ny == 2 && ddy < 0)) continue;  // 2 cells across: the same cell twice
+        int ocx = lcx + ddx, ocy = cy + ddy;
+        if (!g.ghost) {
+            if (ocx < 0) ocx += g.nx; else if (ocx >= g.nx) ocx -= g.nx;
+        }
+        if (ocy < 0) ocy += g.ny; else if (ocy >= g.ny) ocy -= g.ny;
+        const int oc = ocx * g.ny + ocy;
+        const int n = cnt[oc];
+        for (int s = lane; s < n; s += 32) {
+            if (mode == 1 && oc == cell && s == slot) continue;
+            const double2 q = pos[(size_t)oc * g.K + s];
+            const double r2 = exact_r2(pt.x, pt.y, q.x, q.y, g.Lx, g.Ly, hLx, hLy);
+            if (r2 <= r2cut) acc += pair_u<POT>(r2, pp);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        out[0] = mode == 1 ? -acc : acc;
+        out[1] = pt.x;
+        out[2] = pt.y;
+        sel[0] = cell;
+        sel[1] = slot;
+    }
+}
+
+// carries out a probed insertion (what = 1) or deletion (what = 2); err[0] = 1 when the cell is full
+__global__ void k_apply_probe(double2 *pos, int *cnt, int *ids, int K, int what, const double *probe, const int *sel,
+                              double *energy, int *err) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int cell = sel[0];
+    const int n = cnt[cell];
+    if (what == 1) {
+        if (n >= K) {
+            err[0] = 1;
+            return;
+        }
+        pos[(size_t)cell * K + n] = make_double2(probe[1], probe[2]);
+        if (ids) ids[(size_t)cell * K + n] = -1;
+        cnt[cell] = n + 1;
+    } else {
+        const int slot = sel[1];
+        pos[(size_t)cell * K + slot] = pos[(size_t)cell * K + n - 1];
+        if (ids) ids[(size_t)cell * K + slot] = ids[(size_t)cell * K + n - 1];
+        cnt[cell] = n - 1;
+    }
+    energy[0] += probe[0];
+}

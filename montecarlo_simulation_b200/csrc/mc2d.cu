@@ -126,6 +126,9 @@ struct mc2d_ctx {
     int fuse_passes = 1;                      // MC2D_SWEEP_FUSE=0: one launch per colour pass (A-B tests)
     bool auto_margin = false;                 // cell_margin = -1: the cell width is chosen at the first upload
     // NPT volume move in flight (mc2d_rescale_try): the rescaled configuration sits in the spare buffer
+    double *d_probe = nullptr;  // [0] dU, [1] x, [2] y of the last single-particle probe
+    int *d_probe_sel = nullptr;  // [0] stored cell, [1] slot
+    int probe_pending = 0;       // 1: a probed insertion, 2: a probed deletion can be applied
     bool rescale_pending = false;
     Grid rescale_g{};
     double rescale_Lx = 0, rescale_Ly = 0, rescale_U = 0;
@@ -341,6 +344,8 @@ extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
     CU(cudaMalloc(&ctx->d_pair_stats, 4 * sizeof(unsigned long long)));
     CU(cudaMalloc(&ctx->d_err, 4 * sizeof(int)));
     CU(cudaMalloc(&ctx->d_work, 8 * sizeof(int)));
+    CU(cudaMalloc(&ctx->d_probe, 4 * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_probe_sel, 2 * sizeof(int)));
     CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->dev));
     CU(cudaMalloc(&ctx->d_trace_n, sizeof(unsigned long long)));
     CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -388,6 +393,8 @@ extern "C" int mc2d_destroy(mc2d_ctx *ctx) {
         if (ctx->d_pair_stats) cudaFree(ctx->d_pair_stats);
         if (ctx->d_err) cudaFree(ctx->d_err);
         if (ctx->d_work) cudaFree(ctx->d_work);
+        if (ctx->d_probe) cudaFree(ctx->d_probe);
+        if (ctx->d_probe_sel) cudaFree(ctx->d_probe_sel);
         if (ctx->d_trace_n) cudaFree(ctx->d_trace_n);
         if (ctx->ev0) cudaEventDestroy(ctx->ev0);
         if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -735,6 +742,7 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
     ctx->launches++;
     ctx->have_particles = true;
     ctx->rescale_pending = false;
+    ctx->probe_pending = 0;
     ctx->order_valid = false;
     ctx->n_last = kept;
     // The sweep counter (part of every Philox counter) is NOT reset: a context that is re-uploaded
@@ -1024,6 +1032,78 @@ extern "C" int mc2d_total_energy_virial(mc2d_ctx *ctx, int resync, int allreduce
     if (U) *U = u;
     if (W) *W = w;
     if (N) *N = n;
+    return MC2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-particle probes (Gibbs-ensemble particle exchange)
+// ------------------------------------------------------------------------------------------------
+static int probe_common(mc2d_ctx *ctx, int mode, double x, double y, long long index, double *xo, double *yo, double *dU) {
+    if (!ctx->have_particles) FAIL(MC2D_ERR_STATE, "no particles uploaded");
+    if (ctx->prm.nranks != 1) FAIL(MC2D_ERR_INVALID, "single-particle probes need a single-rank context");
+    CU(cudaSetDevice(ctx->dev));
+    ctx->probe_pending = 0;
+    ctx->rescale_pending = false;
+    const Grid &g = ctx->g;
+    const int ncell = g.ncol * g.ny;
+    if (mode == 1) {
+        long long n = 0;
+        if (int rc = count_particles(ctx, &n)) return rc;
+        if (index < 0 || index >= n) FAIL(MC2D_ERR_INVALID, "particle index %lld outside [0, %lld)", index, n);
+        CU(ctx->offsets.ensure(sizeof(int) * (size_t)(ncell + 1)));
+        size_t tmp_bytes = 0;
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->cnt[ctx->cur], ctx->offsets.as<int>(), ncell, ctx->stream));
+        CU(ctx->cub_tmp.ensure(tmp_bytes));
+        CU(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->cnt[ctx->cur], ctx->offsets.as<int>(), ncell,
+                                         ctx->stream));
+        ctx->launches += 2;
+    } else if (!(x >= 0.0 && x < ctx->prm.Lx && y >= 0.0 && y < ctx->prm.Ly)) {
+        FAIL(MC2D_ERR_OUT_OF_BOX, "probe point (%g, %g) outside [0, %g) x [0, %g)", x, y, ctx->prm.Lx, ctx->prm.Ly);
+    }
+    DISPATCH_POT(ctx->prm.potential, {
+        k_probe_slots<POT><<<1, 32, 0, ctx->stream>>>(ctx->pos[ctx->cur], ctx->cnt[ctx->cur], g, ctx->pp, ctx->r2cut, mode,
+                                                      make_double2(x, y), index, ctx->offsets.as<int>(), ctx->d_probe,
+                                                      ctx->d_probe_sel);
+    });
+    ctx->launches++;
+    double h[3];
+    CU(cudaMemcpyAsync(h, ctx->d_probe, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    if (dU) *dU = h[0];
+    if (xo) *xo = h[1];
+    if (yo) *yo = h[2];
+    ctx->probe_pending = mode == 1 ? 2 : 1;
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_probe_point(mc2d_ctx *ctx, double x, double y, double *dU) {
+    if (!ctx) return MC2D_ERR_INVALID;
+    return probe_common(ctx, 0, x, y, 0, nullptr, nullptr, dU);
+}
+
+extern "C" int mc2d_probe_particle(mc2d_ctx *ctx, long long index, double *x, double *y, double *dU) {
+    if (!ctx) return MC2D_ERR_INVALID;
+    return probe_common(ctx, 1, 0.0, 0.0, index, x, y, dU);
+}
+
+extern "C" int mc2d_apply_probe(mc2d_ctx *ctx, int what) {
+    if (!ctx) return MC2D_ERR_INVALID;
+    const int pending = ctx->probe_pending;
+    ctx->probe_pending = 0;
+    if (what == 0) return MC2D_OK;
+    if (what != pending) FAIL(MC2D_ERR_STATE, "no matching probe pending (asked %d, pending %d)", what, pending);
+    CU(cudaSetDevice(ctx->dev));
+    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+    k_apply_probe<<<1, 32, 0, ctx->stream>>>(ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->use_ids ? ctx->ids[ctx->cur] : nullptr,
+                                             ctx->g.K, what, ctx->d_probe, ctx->d_probe_sel, ctx->d_energy, ctx->d_err);
+    ctx->launches++;
+    int full = 0;
+    CU(cudaMemcpyAsync(&full, ctx->d_err, sizeof full, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    if (full) FAIL(MC2D_ERR_CELL_OVERFLOW, "the cell of the inserted particle has no free slot (capacity %d)", ctx->g.K);
+    ctx->n_last += what == 1 ? 1 : -1;
     return MC2D_OK;
 }
 
@@ -1326,6 +1406,7 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
                            long long trace_cap, long long *trace_n) {
     if (!ctx->have_particles) FAIL(MC2D_ERR_STATE, "no particles uploaded");
     ctx->rescale_pending = false;  // the re-bin overwrites the spare buffer
+    ctx->probe_pending = 0;
     if (!plan || plan->disp_per_particle < 0 || plan->gc_per_cell < 0 || plan->disp_per_cell < 0 || nsweeps < 0)
         FAIL(MC2D_ERR_INVALID, "bad sweep plan");
     if (plan->disp_per_particle * 1024LL + plan->disp_per_cell + plan->gc_per_cell >= (1 << 28))

@@ -148,6 +148,63 @@ int main() {
         std::printf("ideal gas z=0.5 V=100: <N> = %.3f (theory 50)\n", mean);
         CHECK(std::fabs(mean - 50.0) < 1.0);
     }
+    // ---- Gibbs ensemble, ideal gas, exchange moves only (equlibratemuVT): N_1 is binomial(N, V_1 / V) ----
+    {
+        SimulationBox b1(30.0, 30.0), b2(30.0, 20.0);
+        std::vector<Particle> P1, P2;
+        initializeParticles(P1, b1, 300, true, 3);
+        initializeParticles(P2, b2, 300, true, 4);
+        ThermodynamicCalculator c1(1.0, 0.0, PotentialType::Ideal, 2.5), c2(1.0, 0.0, PotentialType::Ideal, 2.5);
+        Logging l1("/dev/null", "/dev/null"), l2("/dev/null", "/dev/null");
+        RNG rng(21);
+        GibbsMonteCarlo g(b1, b2, P1, P2, c1, c2, 2.5, 0.3, 0.05, l1, l2, rng);
+        g.equlibratemuVT(4000, 1000000, 1000000);
+        double s1 = 0, s2 = 0;
+        const int samples = 3000;
+        for (int s = 0; s < samples; ++s) {
+            g.equlibratemuVT(20, 1000000, 1000000);
+            const double n1 = (double)g.getNumParticles(0);
+            s1 += n1;
+            s2 += n1 * n1;
+            CHECK(g.getNumParticles(0) + g.getNumParticles(1) == 600);
+        }
+        const double mean = s1 / samples, var = s2 / samples - mean * mean;
+        const double p = 900.0 / 1500.0;
+        std::printf("Gibbs ideal gas: <N_1> = %.2f (theory %.1f), Var N_1 = %.1f (theory %.1f)\n", mean, 600 * p, var,
+                    600 * p * (1 - p));
+        CHECK(std::fabs(mean - 600 * p) < 5.0);
+        CHECK(std::fabs(var / (600 * p * (1 - p)) - 1.0) < 0.25);
+    }
+    // ---- Gibbs ensemble, LJ: full loop (sweeps, exchanges, coupled volume changes); N and V are conserved, the
+    //      running energies track a recomputation on the downloaded configurations ----
+    {
+        SimulationBox b1(24.0, 24.0), b2(24.0, 24.0);
+        std::vector<Particle> P1, P2;
+        for (int i = 0; i < 16; ++i)
+            for (int j = 0; j < 16; ++j) {
+                P1.emplace_back((i + 0.5) * 1.5, (j + 0.5) * 1.5);
+                if ((i + j) % 3 == 0) P2.emplace_back((i + 0.5) * 1.5, (j + 0.5) * 1.5);
+            }
+        const long long Ntot = (long long)(P1.size() + P2.size());
+        ThermodynamicCalculator c1(1.5, 0.0, PotentialType::LennardJones, 2.5), c2(1.5, 0.0, PotentialType::LennardJones, 2.5);
+        Logging l1("/dev/null", "/dev/null"), l2("/dev/null", "/dev/null");
+        RNG rng(33);
+        GibbsMonteCarlo g(b1, b2, P1, P2, c1, c2, 2.5, 0.15, 0.05, l1, l2, rng);
+        g.equlibrateNVT(50, 1000000, 10);
+        g.run(3000, 1000000, 1000000);
+        CHECK(g.getNumParticles(0) + g.getNumParticles(1) == Ntot);
+        CHECK(approx(g.getBox(0).getV() + g.getBox(1).getV(), 2 * 576.0, 1e-9));
+        for (int w = 0; w < 2; ++w) {
+            ThermodynamicCalculator &c = w ? c2 : c1;
+            SimulationBox bw = g.getBox(w);
+            const double U = c.computeTotalEnergyCellList(g.getParticles(w), bw);
+            CHECK(approx(g.getEnergy(w), U, 1e-8));
+            CHECK((long long)g.getParticles(w).size() == g.getNumParticles(w));
+        }
+        std::printf("Gibbs LJ T=1.5: N = %lld / %lld, V = %.1f / %.1f, rho = %.3f / %.3f\n", g.getNumParticles(0),
+                    g.getNumParticles(1), g.getBox(0).getV(), g.getBox(1).getV(), g.getNumParticles(0) / g.getBox(0).getV(),
+                    g.getNumParticles(1) / g.getBox(1).getV());
+    }
     std::printf("%d checks, %d failures\n", checks, failures);
     return failures ? 1 : 0;
 }

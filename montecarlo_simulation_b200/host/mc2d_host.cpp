@@ -623,6 +623,224 @@ bool MonteCarlo::stepCellList() {
 bool MonteCarlo::stepBruteForce() { return stepCellList(); }
 
 // =================================================================================================
+// GibbsMonteCarlo — serial_src/GibbsMC.cpp on two GPU contexts
+// =================================================================================================
+struct GibbsMonteCarlo::Side {
+    SimulationBox box;
+    std::vector<Particle> particles;
+    ThermodynamicCalculator &calc;
+    std::unique_ptr<mc2d::Context> gpu;
+    bool host_stale = false;
+    std::uint64_t seed;
+    int regrids = 0;
+    double rcut, delta;
+
+    Side(const SimulationBox &b, std::vector<Particle> p, ThermodynamicCalculator &c, double rcut_, double delta_,
+         std::uint64_t seed_)
+        : box(b), particles(std::move(p)), calc(c), seed(seed_), rcut(rcut_), delta(delta_) {
+        make_context(box, particles, gpu);
+    }
+    void make_context(const SimulationBox &b, const std::vector<Particle> &p, std::unique_ptr<mc2d::Context> &out) {
+        out.reset(new mc2d::Context(b.getLx(), b.getLy(), rcut, calc.potentialSpec(), calc.getTemperature(), 0.0, delta,
+                                    seed + 0x9E3779B97F4A7C15ull * (std::uint64_t)regrids, 0, 0, 1, 0, kNptCellMargin));
+        out->check(mc2d_upload(out->get(), raw(p), nullptr, (long long)p.size()));
+        ++regrids;
+    }
+    mc2d_stats stats() const {
+        mc2d_stats st{};
+        gpu->check(mc2d_get_stats(gpu->get(), &st));
+        return st;
+    }
+    void sync_host() {
+        if (!host_stale) return;
+        long long n = 0;
+        gpu->check(mc2d_num_particles(gpu->get(), &n));
+        particles.resize((size_t)n);
+        gpu->check(mc2d_download(gpu->get(), reinterpret_cast<double *>(particles.data()), nullptr, n, &n));
+        host_stale = false;
+    }
+    // U of the configuration rescaled to nb; `fresh` is set when the present cell grid cannot serve nb
+    double try_box(const SimulationBox &nb, std::unique_ptr<mc2d::Context> &fresh, std::vector<Particle> &scaled) {
+        double U = 0, W = 0;
+        const int rc = mc2d_rescale_try(gpu->get(), nb.getLx(), nb.getLy(), &U, &W);
+        if (rc == MC2D_ERR_GEOMETRY) {
+            sync_host();
+            scaled = particles;
+            const double rx = nb.getLx() / box.getLx(), ry = nb.getLy() / box.getLy();
+            for (Particle &p : scaled) {
+                p.x *= rx;
+                p.y *= ry;
+                if (p.x >= nb.getLx()) p.x = std::nextafter(nb.getLx(), 0.0);
+                if (p.y >= nb.getLy()) p.y = std::nextafter(nb.getLy(), 0.0);
+            }
+            make_context(nb, scaled, fresh);
+            mc2d_stats st{};
+            fresh->check(mc2d_get_stats(fresh->get(), &st));
+            return st.energy;
+        }
+        gpu->check(rc);
+        return U;
+    }
+    void finish_box(bool accept, const SimulationBox &nb, std::unique_ptr<mc2d::Context> &fresh, std::vector<Particle> &scaled) {
+        if (fresh) {
+            if (accept) {
+                gpu = std::move(fresh);
+                particles = scaled;
+                host_stale = false;
+            }
+        } else {
+            gpu->check(mc2d_rescale_finish(gpu->get(), accept ? 1 : 0));
+            if (accept) host_stale = true;
+        }
+        if (accept) box = nb;
+    }
+};
+
+GibbsMonteCarlo::GibbsMonteCarlo(SimulationBox &box1, SimulationBox &box2, std::vector<Particle> particles1,
+                                 std::vector<Particle> particles2, ThermodynamicCalculator &calc1,
+                                 ThermodynamicCalculator &calc2, double rcut, double delta, double delta_V,
+                                 Logging &logger1, Logging &logger2, RNG &rng)
+    : rng_(rng), rcut_(rcut), delta_(delta), delta_V_(delta_V), beta_(1.0 / calc1.getTemperature()) {
+    const std::uint64_t hi = static_cast<std::uint32_t>(rng.uniformInt(0, INT_MAX));
+    const std::uint64_t lo = static_cast<std::uint32_t>(rng.uniformInt(0, INT_MAX));
+    const std::uint64_t seed = (hi << 32) | lo;
+    s_[0].reset(new Side(box1, std::move(particles1), calc1, rcut, delta, seed));
+    s_[1].reset(new Side(box2, std::move(particles2), calc2, rcut, delta, seed ^ 0xD1B54A32D192ED03ull));
+    logger_[0] = &logger1;
+    logger_[1] = &logger2;
+}
+GibbsMonteCarlo::~GibbsMonteCarlo() = default;
+
+const SimulationBox &GibbsMonteCarlo::getBox(int which) const { return s_[which]->box; }
+long long GibbsMonteCarlo::getNumParticles(int which) const { return s_[which]->stats().n_particles; }
+double GibbsMonteCarlo::getEnergy(int which) const { return s_[which]->stats().energy; }
+const std::vector<Particle> &GibbsMonteCarlo::getParticles(int which) {
+    s_[which]->sync_host();
+    return s_[which]->particles;
+}
+
+void GibbsMonteCarlo::recordObservables() {  // GibbsMC.cpp:467-472
+    for (int w = 0; w < 2; ++w) {
+        s_[w]->sync_host();
+        logger_[w]->logSimulationData(s_[w]->particles, s_[w]->box, s_[w]->calc, static_cast<int>(simulation_step_time));
+        logger_[w]->logPositions_dump(s_[w]->particles, s_[w]->box, static_cast<int>(simulation_step_time));
+    }
+}
+
+// one displacement trial per particle in both boxes (particle_displacement_1/2 x N, GibbsMC.cpp:214-231)
+void GibbsMonteCarlo::sweep_both(long long &acc, long long &tot) {
+    const mc2d_sweep_plan plan{1, 0, 1, 0};
+    for (int w = 0; w < 2; ++w) {
+        const mc2d_stats a = s_[w]->stats();
+        if (a.n_particles == 0) continue;
+        mc2d_stats b{};
+        s_[w]->gpu->check(mc2d_run_sweeps(s_[w]->gpu->get(), 1, &plan, &b));
+        s_[w]->host_stale = true;
+        acc += b.accepted[0] - a.accepted[0];
+        tot += b.attempted[0] - a.attempted[0];
+        simulation_step_time += b.attempted[0] - a.attempted[0];
+    }
+}
+
+// GibbsMC.cpp:340-394: a random point in the receiving box, a random particle of the donor box
+bool GibbsMonteCarlo::particle_exchange() {
+    const int to = rng_.uniform01() > 0.5 ? 0 : 1, from = 1 - to;  // > 0.5: remove from box two, insert into box one
+    Side &T = *s_[to], &F = *s_[from];
+    const double N_from = (double)F.stats().n_particles;
+    if (N_from < 50) return false;
+    const double N_to = (double)T.stats().n_particles;
+    const double x = rng_.uniform(0, T.box.getLx()), y = rng_.uniform(0, T.box.getLy());
+    double dU_to = 0, dU_from = 0, px = 0, py = 0;
+    T.gpu->check(mc2d_probe_point(T.gpu->get(), std::min(x, std::nextafter(T.box.getLx(), 0.0)),
+                                  std::min(y, std::nextafter(T.box.getLy(), 0.0)), &dU_to));
+    (to == 0 ? w_1 : w_2) += T.box.getV() * std::exp(-beta_ * dU_to) / (N_to + 1);
+    const long long idx = rng_.uniformInt(0, (int)N_from - 1);
+    F.gpu->check(mc2d_probe_particle(F.gpu->get(), idx, &px, &py, &dU_from));
+    // Acceptance of moving one particle from box F to box T (Frenkel & Smit, Eq. 8.3.3):
+    //   N_F V_T / ((N_T + 1) V_F) exp(-beta dU).
+    // GibbsMC.cpp:359,382 has the ratio upside down, V_F (N_T + 1) / (V_T (N_F + 1)): with it an ideal gas
+    // collapses into one box.  A reference defect, not copied.
+    const double arg = std::exp(-beta_ * (dU_to + dU_from)) * N_from * T.box.getV() / ((N_to + 1) * F.box.getV());
+    const bool accept = rng_.uniform01() < arg;
+    if (accept) {
+        T.gpu->check(mc2d_apply_probe(T.gpu->get(), 1));
+        F.gpu->check(mc2d_apply_probe(F.gpu->get(), 2));
+        T.host_stale = F.host_stale = true;
+    } else {
+        T.gpu->check(mc2d_apply_probe(T.gpu->get(), 0));
+        F.gpu->check(mc2d_apply_probe(F.gpu->get(), 0));
+    }
+    return accept;
+}
+
+// GibbsMC.cpp:396-460: the total volume is kept, ln(V1 / V2) takes a uniform step of width delta_V
+bool GibbsMonteCarlo::volume_change() {
+    Side &A = *s_[0], &B = *s_[1];
+    const double V1 = A.box.getV(), V2 = B.box.getV();
+    const mc2d_stats sa = A.stats(), sb = B.stats();
+    const double U_old = sa.energy + sb.energy;
+    const double dlnV = rng_.uniform(-0.5, 0.5) * delta_V_;
+    const double q = std::exp(std::log(V1 / V2) + dlnV);
+    const double V1n = (V1 + V2) * q / (1 + q), V2n = (V1 + V2) - V1n;
+    SimulationBox b1 = A.box, b2 = B.box;
+    b1.setV(V1n);
+    b2.setV(V2n);
+    std::unique_ptr<mc2d::Context> f1, f2;
+    std::vector<Particle> sc1, sc2;
+    const double U_new = A.try_box(b1, f1, sc1) + B.try_box(b2, f2, sc2);
+    double arg = std::exp(-beta_ * (U_new - U_old));
+    arg *= std::pow(V1n / V1, (double)sa.n_particles + 1) * std::pow(V2n / V2, (double)sb.n_particles + 1);
+    const bool accept = rng_.uniform01() < arg;
+    A.finish_box(accept, b1, f1, sc1);
+    B.finish_box(accept, b2, f2, sc2);
+    return accept;
+}
+
+int GibbsMonteCarlo::loop(Loop kind, size_t nSteps, size_t fOutputStep, size_t fUpdateCell) {
+    if (fOutputStep == 0 || fUpdateCell == 0) throw std::invalid_argument("output / cell-update period must be > 0");
+    long long acc = 0, tot = 0;
+    for (size_t step = 0; step < nSteps; ++step) {
+        const double r = rng_.uniform01();  // drawn in every loop of the reference, used by two of them
+        bool single = false, ok = false;
+        switch (kind) {
+        case Loop::NVT: sweep_both(acc, tot); break;
+        case Loop::NPT:
+            sweep_both(acc, tot);
+            ok = volume_change();
+            single = true;
+            break;
+        case Loop::muVT:
+            if (r < 0.5) sweep_both(acc, tot);
+            else { ok = particle_exchange(); single = true; }
+            break;
+        case Loop::Gibbs:
+            if (r < 0.5) sweep_both(acc, tot);
+            else if (r < 0.75) { ok = particle_exchange(); single = true; }
+            else { ok = volume_change(); single = true; }
+            break;
+        }
+        if (single) {
+            acc += ok ? 1 : 0;
+            tot += 1;
+            simulation_step_time += 1;
+        }
+        if (step % fUpdateCell == 0) {  // energy re-sync of both boxes (GibbsMC.cpp:249-263)
+            for (int w = 0; w < 2; ++w) {
+                double U, W;
+                long long N;
+                s_[w]->gpu->check(mc2d_total_energy_virial(s_[w]->gpu->get(), 1, 0, &U, &W, &N));
+            }
+        }
+        if ((step + 1) % fOutputStep == 0 || step == nSteps - 1) recordObservables();
+    }
+    return tot > 0 ? static_cast<int>(acc / tot) : 0;  // the reference's integer ratio
+}
+int GibbsMonteCarlo::run(size_t n, size_t fo, size_t fu) { return loop(Loop::Gibbs, n, fo, fu); }
+int GibbsMonteCarlo::equlibrateNVT(size_t n, size_t fo, size_t fu) { return loop(Loop::NVT, n, fo, fu); }
+int GibbsMonteCarlo::equlibrateNPT(size_t n, size_t fo, size_t fu) { return loop(Loop::NPT, n, fo, fu); }
+int GibbsMonteCarlo::equlibratemuVT(size_t n, size_t fo, size_t fu) { return loop(Loop::muVT, n, fo, fu); }
+
+// =================================================================================================
 // MonteCarloNVT_Slabs — MonteCarloNVT_MPI (mpi_src/MC_parallel.cpp) on one GPU per rank
 // =================================================================================================
 MonteCarloNVT_Slabs::MonteCarloNVT_Slabs(int rank, int nranks, int device, SimulationBox &box,

@@ -251,6 +251,42 @@ private:
     void regrid(const SimulationBox &nb, std::unique_ptr<mc2d::Context> &out, std::vector<Particle> &scaled);
 };
 
+// ---- serial_src/GibbsMC.h ------------------------------------------------------------------------------------------
+// Two boxes, each resident on the GPU in its own context.  A step is, as in GibbsMC.cpp:207-270, with probability
+// 1/2 a displacement sweep of both boxes, 1/4 one particle exchange, 1/4 one coupled volume change; the
+// exchange uses mc2d_probe_point / mc2d_probe_particle / mc2d_apply_probe, the volume change mc2d_rescale_*.
+class GibbsMonteCarlo {
+public:
+    GibbsMonteCarlo(SimulationBox &box1, SimulationBox &box2, std::vector<Particle> particles1,
+                    std::vector<Particle> particles2, ThermodynamicCalculator &calc1, ThermodynamicCalculator &calc2,
+                    double rcut, double delta, double delta_V, Logging &logger1, Logging &logger2, RNG &rng);
+    ~GibbsMonteCarlo();
+    int run(size_t nSteps, size_t fOutputStep, size_t fUpdateCell);
+    int equlibrateNVT(size_t nSteps, size_t fOutputStep, size_t fUpdateCell);
+    int equlibrateNPT(size_t nSteps, size_t fOutputStep, size_t fUpdateCell);
+    int equlibratemuVT(size_t nSteps, size_t fOutputStep, size_t fUpdateCell);
+    double w_1 = 0, w_2 = 0;  // Widom accumulators of the exchange move (GibbsMC.cpp:352,375)
+    // state, for tests and drivers
+    const SimulationBox &getBox(int which) const;
+    long long getNumParticles(int which) const;
+    double getEnergy(int which) const;
+    const std::vector<Particle> &getParticles(int which);
+    bool particle_exchange();
+    bool volume_change();
+
+private:
+    struct Side;
+    std::unique_ptr<Side> s_[2];
+    Logging *logger_[2];
+    RNG &rng_;
+    double rcut_, delta_, delta_V_, beta_;
+    long long simulation_step_time = 0;
+    enum class Loop { NVT, NPT, muVT, Gibbs };
+    int loop(Loop kind, size_t nSteps, size_t fOutputStep, size_t fUpdateCell);
+    void sweep_both(long long &acc, long long &tot);
+    void recordObservables();
+};
+
 // ---- mpi_src/MC_parallel.h (MonteCarloNVT_MPI) on GPU slabs ---------------------------------------------------------
 // One object per rank / GPU.  The communicator bootstrap is a callback that broadcasts a byte buffer
 // from rank 0 (MPI_Bcast in the reference's world), so this header needs no MPI.

@@ -40,10 +40,8 @@ int main(int argc, char *argv[]) {
         if (ensemble_name == "NVT") ensemble = Ensemble::NVT;
         else if (ensemble_name == "GCMC" || ensemble_name.empty()) ensemble = Ensemble::GCMC;
         else if (ensemble_name == "NPT") ensemble = Ensemble::NPT;
-        else if (ensemble_name == "Gibbs") {
-            std::cerr << "Error: ensemble " << ensemble_name << " is not on the GPU hot path" << std::endl;
-            return 1;
-        } else {
+        else if (ensemble_name == "Gibbs") ensemble = Ensemble::Gibbs;
+        else {
             std::cerr << "Error: Unrecognised ensemble" << std::endl;
             return 1;
         }
@@ -60,6 +58,39 @@ int main(int argc, char *argv[]) {
                   << "ensemble = " << (ensemble_name.empty() ? "[default GCMC]" : ensemble_name) << "\n"
                   << "Output XYZ = " << out_xyz << ", Output Data = " << out_data << "\n"
                   << std::endl;
+
+        if (ensemble == Ensemble::Gibbs) {  // serial_src/main.cpp:146-236: a second box from the keys Lx2 Ly2 N2 ...
+            const double Lx2 = input.getConstant("Lx2"), Ly2 = input.getConstant("Ly2");
+            const int N2 = static_cast<int>(input.getConstant("N2"));
+            const std::string out_xyz2 = input.getFilename("out_xyz2"), out_data2 = input.getFilename("out_data2");
+            const std::string position_file2 = input.getFilename("position_file2");
+            std::cout << "Lx_2 = " << Lx2 << ", Ly_2 = " << Ly2 << ", N_2 = " << N2 << "\nOutput XYZ 2 = " << out_xyz2
+                      << ", Output Data 2 = " << out_data2 << "\n" << std::endl;
+            SimulationBox box_1(Lx, Ly), box_2(Lx2, Ly2);
+            std::vector<Particle> particles_1, particles_2;
+            if (!position_file.empty()) initializeParticles_from_file(particles_1, box_1, N, position_file);
+            else initializeParticles(particles_1, box_1, N, true, seed * 10);
+            if (!position_file2.empty()) initializeParticles_from_file(particles_2, box_2, N2, position_file2);
+            else initializeParticles(particles_2, box_2, N2, true, seed * 5);
+            Logging logger_1(out_xyz, out_data), logger_2(out_xyz2, out_data2);
+            RNG rng(seed);
+            const PotentialType pt = selectPotentialType(potentialName);
+            ThermodynamicCalculator calc_1(T, pressure, pt, rcut, mu, f, alpha, A_0, kappa);
+            ThermodynamicCalculator calc_2(T, pressure, pt, rcut, mu, f, alpha, A_0, kappa);
+            GibbsMonteCarlo gmc(box_1, box_2, particles_1, particles_2, calc_1, calc_2, rcut, delta, delta_V, logger_1,
+                                logger_2, rng);
+            const size_t upd = cellUpdateFreq >= 1 ? static_cast<size_t>(cellUpdateFreq) : 1;
+            std::cout << "Equilibration:" << std::endl;
+            if (eSteps >= 1) {
+                gmc.equlibrateNVT(static_cast<size_t>(eSteps + 1), static_cast<size_t>(eSteps), upd);
+                gmc.equlibratemuVT(static_cast<size_t>(eSteps + 1), static_cast<size_t>(eSteps), upd);
+            }
+            std::cout << "Running:" << std::endl;
+            gmc.run(static_cast<size_t>(nSteps), outputFreq >= 1 ? static_cast<size_t>(outputFreq) : 1, upd);
+            std::cout << "Simulation completed. N = " << gmc.getNumParticles(0) << " / " << gmc.getNumParticles(1)
+                      << ", V = " << gmc.getBox(0).getV() << " / " << gmc.getBox(1).getV() << std::endl;
+            return 0;
+        }
 
         SimulationBox box(Lx, Ly);
         std::vector<Particle> particles;

@@ -96,10 +96,10 @@ def test_input_txt_driver_and_log_formats(host_built, tmp_path):
     last = max(i for i, l in enumerate(dump) if l == "ITEM: NUMBER OF ATOMS")
     assert int(dump[last + 1]) == n and len(dump) - (last + 7) == n
     assert dump[last + 7].split()[0] == "1" and dump[last + 7].split()[3] == "0"
-    # the Gibbs ensemble is refused loudly
-    inp.write_text(inp.read_text().replace("ensemble GCMC", "ensemble Gibbs"))
+    # an unknown ensemble is refused loudly
+    inp.write_text(inp.read_text().replace("ensemble GCMC", "ensemble muPT"))
     bad = subprocess.run([os.path.join(host_built, "mc2d_serial"), str(inp)], capture_output=True, text=True)
-    assert bad.returncode == 1 and "not on the GPU hot path" in bad.stderr
+    assert bad.returncode == 1 and "Unrecognised ensemble" in bad.stderr
 
 
 def test_slab_driver_and_log_formats(host_built, tmp_path):
@@ -159,3 +159,26 @@ def test_input_txt_driver_npt(host_built, tmp_path):
     last = max(i for i, l in enumerate(dump) if l == "ITEM: BOX BOUNDS pp pp ff")
     Lx = float(dump[last + 1].split()[1])
     assert abs(Lx * Lx - vols[-1]) < 1e-3 * vols[-1]
+
+
+def test_input_txt_driver_gibbs(host_built, tmp_path):
+    """`ensemble Gibbs` (serial_src/main.cpp:146-236): two boxes from Lx2 Ly2 N2 out_xyz2 out_data2; particles and
+    total volume are conserved, both logs are written in the reference's format."""
+    inp = tmp_path / "input.txt"
+    inp.write_text("\n".join([
+        "Lx 30.0", "Ly 30.0", "N 300", "Lx2 30.0", "Ly2 30.0", "N2 120", "rcut 2.5", "T 1.5", "delta_V 0.05",
+        "nSteps 400", "eSteps 50", "outputFreq 100", "cellUpdateFreq 10", "delta 0.2", "seed 5",
+        "potential WCA", "ensemble Gibbs",
+        "out_xyz %s" % (tmp_path / "t1.dump"), "out_data %s" % (tmp_path / "d1.log"),
+        "out_xyz2 %s" % (tmp_path / "t2.dump"), "out_data2 %s" % (tmp_path / "d2.log"), ""]))
+    out = subprocess.run([os.path.join(host_built, "mc2d_serial"), str(inp)], capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    last = []
+    for name in ("d1.log", "d2.log"):
+        rows = (tmp_path / name).read_text().strip().splitlines()
+        assert len(rows) >= 4
+        f = dict(kv.strip().split(":") for kv in rows[-1].replace("\t", "").split(","))
+        last.append((int(f["NumberofParticles"]), float(f["Volume"])))
+    assert last[0][0] + last[1][0] == 420
+    assert abs(last[0][1] + last[1][1] - 1800.0) < 1e-3

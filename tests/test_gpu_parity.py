@@ -675,3 +675,46 @@ def test_auto_cell_width_for_short_range_potentials(mc, oracle):
         st = ctx.run_sweeps(10, gc_per_cell=1)
         out = ctx.download()
         assert relerr(st["energy"], oracle.total_energy_celllist(calc, L, L, out)) < 1e-9
+
+
+def test_single_particle_probes_match_oracle(mc, oracle):
+    """mc2d_probe_point / mc2d_probe_particle / mc2d_apply_probe (the Gibbs-ensemble exchange move, GibbsMC.cpp:340-394):
+    energies equal the oracle's getNeighbors2 / getNeighbors + computeLocalEnergy on the downloaded configuration;
+    applying them inserts / deletes exactly that particle and moves the running energy by exactly dU."""
+    Lx, Ly = 47.0, 39.0
+    xy = lattice(30, 26, Lx, Ly, 0.2, 9)
+    calc = oracle.calc(1.0, 0.0, ol.LJ, 2.5)
+    rng = np.random.default_rng(4)
+    with mc.Context(Lx, Ly, 2.5, T=1.0, delta=0.1, seed=8) as ctx:
+        ctx.upload(xy)
+        ctx.run_sweeps(7)  # a shifted grid, as in a running simulation
+        cfg = ctx.download()
+        for _ in range(20):
+            x, y = rng.uniform(0, Lx), rng.uniform(0, Ly)
+            assert relerr(ctx.probe_point(x, y), oracle.point_energy(calc, Lx, Ly, cfg, x, y)) < REL
+            i = int(rng.integers(len(cfg)))
+            px, py, dU = ctx.probe_particle(i)
+            assert (px, py) == tuple(cfg[i])
+            assert relerr(dU, -oracle.local_energy(calc, Lx, Ly, cfg, i)) < REL
+        ctx.apply_probe(0)
+        U0 = ctx.stats()["energy"]
+        x, y = 13.37, 21.5
+        dU = ctx.probe_point(x, y)
+        ctx.apply_probe(1)
+        after = ctx.download()
+        assert len(after) == len(cfg) + 1 and ((after == [x, y]).all(axis=1)).sum() == 1
+        assert ctx.stats()["energy"] == U0 + dU
+        assert relerr(ctx.stats()["energy"], oracle.total_energy_celllist(calc, Lx, Ly, after)) < 1e-9
+        j = 123
+        px, py, dU2 = ctx.probe_particle(j)
+        assert (px, py) == tuple(after[j])
+        ctx.apply_probe(2)
+        final = ctx.download()
+        assert len(final) == len(cfg) and not ((final == [px, py]).all(axis=1)).any()
+        assert relerr(ctx.stats()["energy"], oracle.total_energy_celllist(calc, Lx, Ly, final)) < 1e-9
+        with pytest.raises(mc.MC2DError):
+            ctx.apply_probe(1)  # nothing pending
+        with pytest.raises(mc.MC2DError):
+            ctx.probe_particle(len(final))
+        st = ctx.run_sweeps(3)
+        assert relerr(st["energy"], oracle.total_energy_celllist(calc, Lx, Ly, ctx.download())) < 1e-9
