@@ -503,7 +503,7 @@ void MonteCarlo::recordObservables() {
 
 int MonteCarlo::run(size_t nSteps, size_t fOutputStep, size_t fUpdateCell) {
     if (fOutputStep == 0 || fUpdateCell == 0) throw std::invalid_argument("output / cell-update period must be > 0");
-    const mc2d_sweep_plan plan{1, ensemble_ == Ensemble::GCMC ? gc_per_cell_ : 0, 1};
+    const mc2d_sweep_plan plan{1, ensemble_ == Ensemble::GCMC ? gc_per_cell_ : 0, 1, 0};
     const mc2d_stats before = stats();
     mc2d_stats st = before;
     size_t step = 0;
@@ -614,7 +614,7 @@ bool MonteCarlo::nptMove() {
 }
 
 bool MonteCarlo::stepCellList() {
-    const mc2d_sweep_plan plan{1, 0, 1};
+    const mc2d_sweep_plan plan{1, 0, 1, 0};
     mc2d_stats a = stats(), b{};
     gpu_->check(mc2d_run_sweeps(gpu_->get(), 1, &plan, &b));
     host_stale_ = true;
@@ -861,7 +861,7 @@ MonteCarloNVT_Slabs::MonteCarloNVT_Slabs(int rank, int nranks, int device, Simul
 MonteCarloNVT_Slabs::~MonteCarloNVT_Slabs() = default;
 
 double MonteCarloNVT_Slabs::run(std::size_t nsweeps, int) {
-    const mc2d_sweep_plan plan{1, p_.gc_per_cell, 1};
+    const mc2d_sweep_plan plan{1, p_.gc_per_cell, 1, 0};
     mc2d_stats st{};
     gpu_->check(mc2d_run_sweeps(gpu_->get(), (long long)nsweeps, &plan, &st));
     gpu_->check(mc2d_allreduce_stats(gpu_->get(), &st));  // MC_parallel.cpp:111-112
