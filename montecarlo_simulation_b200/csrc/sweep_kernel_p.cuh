@@ -267,6 +267,10 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
     const double escale = pair_scale<POT>();
 
     unsigned int c_att[3] = {0, 0, 0}, c_acc[3] = {0, 0, 0}, c_ovf = 0;
+#ifdef MC2D_PROFILE_WAIT  // -DMC2D_PROFILE_WAIT: a few warps print where their cycles went (profiles/r01_notes.md)
+    long long prof_wait = 0, prof_items = 0, prof_bar = 0;
+    const long long prof_t0 = clock64();
+#endif
 
     // ---- work distribution and prefetch ----
     // Warp w starts with item w of the heavy-first list (a fixed first item: thousands of warps asking one address
@@ -350,7 +354,13 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
     int it0 = blockIdx.x * wpb + wib;
     int acx = 0, it0_rank = 0;  // column pair of the current item and its rank inside the pair
     const int acy0 = load_perm(it0, acx, it0_rank);  // the order does not change during a sweep: fetched before the barrier
+#ifdef MC2D_PROFILE_WAIT
+    const long long pb0 = clock64();
+#endif
     if (ps > 0) cooperative_groups::this_grid().sync();  // the cells of the previous colour are written
+#ifdef MC2D_PROFILE_WAIT
+    prof_bar += clock64() - pb0;
+#endif
     if (a.halo_fused && it0 < ipp) {  // boundary item: wait until the neighbour has completed the ghost column it reads
         if (lane == 0) {
             const volatile unsigned long long *f = a.myflag;
@@ -430,8 +440,15 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                     }
                 }
             }
+#ifdef MC2D_PROFILE_WAIT
+            const long long pw0 = clock64();
+#endif
             cp_async_wait_all();
             __syncwarp();
+#ifdef MC2D_PROFILE_WAIT
+            prof_wait += clock64() - pw0;
+            prof_items += 1;
+#endif
             if (!have_it1) {  // the ticket has arrived by now; the sorted cell of the next item travels during the rounds
                 it1 = __shfl_sync(FULL_MASK, tick, 0);
                 acy1 = load_perm(it1, acx1, rank1);
@@ -640,6 +657,11 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
     }
   }
 
+#ifdef MC2D_PROFILE_WAIT
+    if (lane == 0 && (blockIdx.x * wpb + wib) % 601 == 0)
+        printf("warp %d: total %lld cycles, staging wait %lld (%lld items), grid barrier %lld\n", blockIdx.x * wpb + wib,
+               clock64() - prof_t0, prof_wait, prof_items, prof_bar);
+#endif
     // ---- epilogue: move counters ----
     unsigned int cw[7] = {c_att[0], c_att[1], c_att[2], c_acc[0], c_acc[1], c_acc[2], c_ovf};
 #pragma unroll
