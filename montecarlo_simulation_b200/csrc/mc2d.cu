@@ -139,6 +139,8 @@ struct mc2d_ctx {
     int *d_err = nullptr;                      // [0] overflow need, [1] flags, [2] max count
     DevBuf partial, trace_buf;
     DevBuf order_buf;  // work order of k_sweep_p (k_order_local), rebuilt after every re-bin
+    DevBuf done_buf;   // k_sweep_p pipeline: finished items per (colour pass, column pair)
+    int pipeline = 1;  // MC2D_SWEEP_PIPELINE=0: grid barrier between the colours of a fused sweep (A-B tests)
     bool order_valid = false;
     int *d_work = nullptr;  // work-item ticket counters: [p] interior / whole pass p of a sweep, [4 + p] slab boundary
     int num_sms = 0;
@@ -386,7 +388,7 @@ extern "C" int mc2d_destroy(mc2d_ctx *ctx) {
         free_slots(ctx);
         DevBuf *bufs[] = {&ctx->partial, &ctx->trace_buf, &ctx->xy_in, &ctx->ids_in, &ctx->keys, &ctx->keys_sorted,
                           &ctx->idx, &ctx->idx_sorted, &ctx->spos, &ctx->sids, &ctx->start, &ctx->cub_tmp, &ctx->pts,
-                          &ctx->excl, &ctx->outE, &ctx->outC, &ctx->outI, &ctx->offsets, &ctx->order_buf};
+                          &ctx->excl, &ctx->outE, &ctx->outC, &ctx->outI, &ctx->offsets, &ctx->order_buf, &ctx->done_buf};
         for (DevBuf *b : bufs) b->release();
         if (ctx->d_counters) cudaFree(ctx->d_counters);
         if (ctx->d_energy) cudaFree(ctx->d_energy);
@@ -1470,6 +1472,7 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     if (const char *e = getenv("MC2D_REBIN_G")) rebin_G = atoi(e);
     ctx->kev_kind.clear();
     if (const char *e = getenv("MC2D_SWEEP_FUSE")) ctx->fuse_passes = atoi(e);
+    if (const char *e = getenv("MC2D_SWEEP_PIPELINE")) ctx->pipeline = atoi(e);
     CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     // Slab mode with peer-memory halos: the boundary column pair of a pass (and the two boundary columns of
@@ -1557,6 +1560,8 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             if (!ctx->order_valid)
                 if (int rc = build_order(ctx)) return rc;
             CU(cudaMemsetAsync(ctx->d_work, 0, 8 * sizeof(int), ctx->stream));
+            CU(ctx->done_buf.ensure(sizeof(int) * 4 * (size_t)npairs));
+            CU(cudaMemsetAsync(ctx->done_buf.p, 0, sizeof(int) * 4 * (size_t)npairs, ctx->stream));
         }
         // single rank / no overlap: the four passes of a sweep go out as ONE cooperative launch (grid barrier between
         // colours); MC2D_SWEEP_FUSE=0 launches them one by one
@@ -1577,6 +1582,8 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             a.npass = (fuse || fuse_halo) ? 4 : 1;
             for (int q = 0; q < 4; ++q) a.colours[q] = order[q];
             a.dU_stride = nblocks;
+            a.pipeline = (fuse && ctx->pipeline) ? 1 : 0;
+            a.done = ctx->done_buf.as<int>();
             a.halo_fused = 0;
             a.myflag = nullptr;
             a.seq_base = 0;

@@ -31,6 +31,8 @@ struct SweepArgs {
     int npass;            // k_sweep_p: colour passes done by this launch: 1, or 4 with a grid barrier in between
     int colours[4];       //            their colours (npass > 1); pass p uses work[p] and partial_dU + p * dU_stride
     int dU_stride;
+    int pipeline;         // k_sweep_p, npass = 4, single rank: no grid barrier; items of all colours in one list
+    int *done;            //            (colour-major, then column pair), done[pass][pair] finished items gate the next colour
     // k_sweep_p, slab mode with all passes in one launch: the halo is part of the kernel (sweep_kernel_p.cuh)
     int halo_fused;
     double2 *hpos[2];                // [0] left neighbour's right-ghost column, [1] right neighbour's left-ghost column

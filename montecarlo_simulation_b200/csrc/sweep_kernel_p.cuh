@@ -9,10 +9,15 @@
 //    (occupancy, candidate count).  A work item is 32/G consecutive cells of that order, so the
 //    32/G groups of a warp run the same number of displacement rounds and candidate iterations
 //    (in grid order a warp ran max-of-8 Poisson rounds: half of the lanes idle).
-//  * Items are numbered heavy-first (rank-major over the column pairs) and handed out through one
-//    atomic counter per pass to 148 x 3 resident CTAs: no CTA-launch / CTA-tail cost per item, and
-//    the warps of an SM drift out of phase, so the global-memory latency of one warp's staging
-//    hides behind the arithmetic of the others.
+//  * Items are handed out through an atomic ticket counter to 148 x 3 resident CTAs: no CTA-launch /
+//    CTA-tail cost per item, and the warps of an SM drift out of phase, so the global-memory latency
+//    of one warp's staging hides behind the arithmetic of the others.
+//  * One launch does the four colour passes of a sweep.  Single rank: the items of all colours are ONE
+//    list (colour-major, then column pair, heavy-first inside a pair); an item of colour p+1 in
+//    column pair P waits — between items, never inside one — until the items of colour p in the
+//    pairs P-1, P, P+1 are finished (per-pair completion counters, ld.acquire.gpu).  No grid barrier:
+//    the tail of a colour overlaps the head of the next.  Slab / single-pass launches: items of one
+//    colour, heavy-first over all pairs, grid barrier between colours.
 //  * The index chain of an item (work ticket -> sorted cell -> 9 cell counts) is prefetched into
 //    registers while the previous items run: staging starts with the position loads.
 //
@@ -297,9 +302,24 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
             rem -= div_n;
         }
     };
-    auto split = [&](int item, int &p, int &r) {
+    const unsigned div_i = (unsigned)ipp, div_i_inv = 0xFFFFFFFFu / div_i;
+    // pass of an item: the loop variable, or (pipeline) the colour-major position in the list of all four colours
+    auto pass_of = [&](int item, int ps_loop) {
+        return a.pipeline ? (int)(item >= a.nitems) + (int)(item >= 2 * a.nitems) + (int)(item >= 3 * a.nitems) : ps_loop;
+    };
+    auto split = [&](int item, int psv, int &p, int &r) {
         unsigned q, rem;
-        if (a.halo_fused) {
+        if (a.pipeline) {  // pair-major inside a colour: early pairs finish early and release the next colour
+            const unsigned idx = (unsigned)(item - psv * a.nitems);
+            q = __umulhi(idx, div_i_inv);
+            rem = idx - q * div_i;
+            if (rem >= div_i) {
+                ++q;
+                rem -= div_i;
+            }
+            p = (int)q;
+            r = (int)rem;
+        } else if (a.halo_fused) {
             if (item < ipp) {
                 p = bpair;
                 r = item;
@@ -314,19 +334,30 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
             r = (int)q;
         }
     };
-    auto load_perm = [&](int item, int &p, int &r) {  // -> acy of this group's cell (or -1); the item's pair and rank
-        split(item, p, r);
+    const int n_all = a.pipeline ? a.npass * a.nitems : a.nitems;
+    auto colour_of = [&](int psv) { return a.npass > 1 ? a.colours[psv] : a.colour; };
+    // -> acy of this group's cell (or -1); the item's pass, pair and rank
+    auto load_perm = [&](int item, int ps_loop, int &psv, int &p, int &r) {
+        psv = item < n_all ? pass_of(item, ps_loop) : ps_loop;
+        if (item >= n_all) {
+            p = 0;
+            r = 0;
+            return -1;
+        }
+        split(item, psv, p, r);
         const int j = r * GPW + gi;
-        return (item < a.nitems && j < nay) ? perm[(size_t)p * nay + j] : -1;
+        const int *pm = a.order + (size_t)colour_of(psv) * npairs * nay;
+        return (j < nay) ? pm[(size_t)p * nay + j] : -1;
     };
-    auto load_counts = [&](int p, int acy, bool past_l1) {
+    auto load_counts = [&](int psv, int p, int acy, bool past_l1) {
         ItemMeta m;
         m.acy = acy;
         m.n_own = 0;
         m.c_lo = m.c_hi = 0;
         if (acy >= 0) {
+            const int c = colour_of(psv);
             int col3[3], row3[3];
-            nbr_rows_cols(g, g.ghost + 2 * p + px, 2 * acy + py, col3, row3);
+            nbr_rows_cols(g, g.ghost + 2 * p + (c & 1), 2 * acy + (c >> 1), col3, row3);
             m.n_own = a.cnt[col3[1] + row3[1]];
             if (POT != POT_IDEAL) {
 #pragma unroll
@@ -341,19 +372,40 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         }
         return m;
     };
-  for (int ps = 0; ps < a.npass; ++ps) {
-    const int colour = a.npass > 1 ? a.colours[ps] : a.colour;
-    px = colour & 1;
-    py = colour >> 1;
-    perm = a.order + (size_t)colour * npairs * nay;
+    // pipeline: an item of colour pass psv > 0 in column pair p reads cells that the previous colour pass wrote in the
+    // pairs p-1, p, p+1: wait until all their items are finished.  ld.acquire.gpu also drops this SM's L1 copies.
+    // block = false: one look (used while the current item is still open: it may itself be one of the items the next
+    // one waits for, so blocking there would deadlock); block = true: spin (between items only).
+    auto wait_deps = [&](int psv, int p, bool block) {
+        if (!a.pipeline || psv == 0) return true;
+        const int *d = a.done + (psv - 1) * npairs;
+        const int pm = p == 0 ? npairs - 1 : p - 1, pp = p == npairs - 1 ? 0 : p + 1;
+        for (;;) {
+            int v0, v1, v2;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v0) : "l"(d + pm) : "memory");
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v1) : "l"(d + p) : "memory");
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v2) : "l"(d + pp) : "memory");
+            if (min(v0, min(v1, v2)) >= ipp) return true;
+            if (!block) return false;
+            __nanosleep(64);
+        }
+    };
+    auto set_pass = [&](int psv) {
+        const int colour = colour_of(psv);
+        px = colour & 1;
+        py = colour >> 1;
+        perm = a.order + (size_t)colour * npairs * nay;
+        pdU = a.partial_dU + (size_t)psv * a.dU_stride;
+        pass_no = a.pass + psv;
+    };
+  for (int ps = 0; ps < (a.pipeline ? 1 : a.npass); ++ps) {
+    set_pass(ps);
     work = a.work + ps;
-    pdU = a.partial_dU + (size_t)ps * a.dU_stride;
-    pass_no = a.pass + ps;
     bpair = (px == 0) ? 0 : npairs - 1;   // even columns active: the first owned column is the one at the slab edge
     const int hside = (px == 0) ? 0 : 1;  // ... it reads the left ghost and is pushed to the left neighbour
     int it0 = blockIdx.x * wpb + wib;
-    int acx = 0, it0_rank = 0;  // column pair of the current item and its rank inside the pair
-    const int acy0 = load_perm(it0, acx, it0_rank);  // the order does not change during a sweep: fetched before the barrier
+    int acx = 0, it0_rank = 0, ps0 = ps;  // column pair of the current item, its rank inside the pair, its colour pass
+    const int acy0 = load_perm(it0, ps, ps0, acx, it0_rank);  // the order does not change during a sweep: fetched before the barrier
 #ifdef MC2D_PROFILE_WAIT
     const long long pb0 = clock64();
 #endif
@@ -369,11 +421,13 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         __syncwarp();
         __threadfence();
     }
-    ItemMeta m0 = load_counts(acx, acy0, a.halo_fused && it0 < ipp);
+    wait_deps(ps0, acx, true);  // (pipeline: the first item of a warp belongs to the first colour unless the grid is tiny)
+    ItemMeta m0 = load_counts(ps0, acx, acy0, a.halo_fused && it0 < ipp);
 
-    while (it0 < a.nitems) {
+    while (it0 < n_all) {
+        if (a.pipeline) set_pass(ps0);
         const int tick = ticket();  // in flight during the staging of this item
-        int it1 = 0, acy1 = -1, acx1 = 0, rank1 = 0;
+        int it1 = 0, acy1 = -1, acx1 = 0, rank1 = 0, ps1 = ps;
         ItemMeta m1;
         bool have_it1 = false, have_m1 = false;
 
@@ -451,7 +505,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
 #endif
             if (!have_it1) {  // the ticket has arrived by now; the sorted cell of the next item travels during the rounds
                 it1 = __shfl_sync(FULL_MASK, tick, 0);
-                acy1 = load_perm(it1, acx1, rank1);
+                acy1 = load_perm(it1, ps, ps1, acx1, rank1);
                 have_it1 = true;
             }
             // to cell-local coordinates, in place
@@ -523,8 +577,10 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                 }
             }
 
-            if (!have_m1) {  // the counts of the next item travel during the GC rounds and the write-back
-                m1 = load_counts(acx1, acy1, false);  // tickets start behind the boundary items
+            // the counts of the next item travel during the GC rounds and the write-back (pipeline: only if the cells
+            // it reads are final already; otherwise after this item is finished)
+            if (!have_m1 && wait_deps(ps1, acx1, false)) {
+                m1 = load_counts(ps1, acx1, acy1, false);  // tickets start behind the boundary items
                 have_m1 = true;
             }
 
@@ -633,6 +689,22 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         // energy change of this item, summed in lane order; the slot is private to the item
         const double dU_w = warp_sum(dU_total);
         if (lane == 0) pdU[it0_rank * npairs + acx] += dU_w;  // the item's slot in the full list
+        if (a.pipeline) {  // this item's cells are written: one more finished item of (colour pass, column pair)
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(&a.done[ps0 * npairs + acx], 1);
+            if (!have_m1) {
+#ifdef MC2D_PROFILE_WAIT
+                const long long pd0 = clock64();
+#endif
+                wait_deps(ps1, acx1, true);
+#ifdef MC2D_PROFILE_WAIT
+                prof_bar += clock64() - pd0;
+#endif
+                m1 = load_counts(ps1, acx1, acy1, false);
+                have_m1 = true;
+            }
+        }
         if (bitem) {  // one more boundary item done; the last one signals both neighbours
             __threadfence_system();
             __syncwarp();
@@ -653,6 +725,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         it0 = it1;
         acx = acx1;
         it0_rank = rank1;
+        ps0 = ps1;
         m0 = m1;
     }
   }

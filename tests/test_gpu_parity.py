@@ -499,10 +499,13 @@ def test_sweep_kernel_variants_are_bit_identical(mc, monkeypatch):
     Lx, Ly = 61.0, 47.5
     xy = lattice(40, 32, Lx, Ly, 0.2, 3)
     res = {}
-    variants = ["0", "4", "8", "4", "2", "4/unfused"]  # last: one launch per colour pass instead of one per sweep
+    # "/unfused": one launch per colour pass instead of one per sweep; "/barrier": one launch per sweep with a grid
+    # barrier between the colours instead of the per-column-pair completion counters
+    variants = ["0", "4", "8", "4", "2", "4/unfused", "4/barrier"]
     for n, G in enumerate(variants):
         monkeypatch.setenv("MC2D_SWEEP_G", G.split("/")[0])
         monkeypatch.setenv("MC2D_SWEEP_FUSE", "0" if "unfused" in G else "1")
+        monkeypatch.setenv("MC2D_SWEEP_PIPELINE", "0" if "barrier" in G else "1")
         with mc.Context(Lx, Ly, 2.5, T=0.9, activity=0.3, delta=0.12, seed=21) as ctx:
             ctx.upload(xy, np.arange(len(xy), dtype=np.int32))
             st = ctx.run_sweeps(12, gc_per_cell=2)
