@@ -344,6 +344,29 @@ def main():
                 "rebin_ms_per_launch": info.k_rebin_ms / max(info.k_rebin_launches, 1),
                 "halo_ms_per_sync": (info.k_halo_ms / info.k_halo_launches) if info.k_halo_launches else None,
                 "note": "path is fp64-ALU/latency bound, not HBM bound (DESIGN.md §4): low HBM fraction expected"}
+    # ---- compute roofline (fp64): algorithmic flops of one colour pass against the MEASURED fp64 FMA peak ----
+    # Algorithmic flops: a displacement evaluates two positions, an insertion / deletion one; a
+    # position costs (distance tests of the 3x3 neighbourhood) x 8 flop + (pairs inside the cutoff) x 14 flop.  The
+    # per-particle test and pair counts come from the energy kernel's counters of the timed steps (its half shell
+    # visits every unordered pair once, so a particle's full neighbourhood is twice the per-particle average).
+    fp64_roof = None
+    try:
+        peak64 = ctx.measure_fp64_peak()
+        n_loc_now = max(ctx.num_particles(), 1)
+        tests_pp = 2.0 * pair_tests / max(args.steps, 1) / n_loc_now
+        evals_pp = 2.0 * pair_evals / max(args.steps, 1) / n_loc_now
+        flop_pos = 8.0 * tests_pp + 14.0 * evals_pp
+        flops_launch = (2.0 * flop_pos * st_r["attempted"][0] + flop_pos * (st_r["attempted"][1] + st_r["attempted"][2])) / nl
+        ach64 = flops_launch / (k_ms * 1e-3) / 1e12
+        fp64_roof = {"bound": "fp64", "achieved": ach64, "peak": peak64, "unit": "TFLOP/s", "frac": ach64 / peak64,
+                     "peak_source": "measured here (mc2d_measure_fp64_peak: independent DFMA chains on every SM)",
+                     "flop_per_position": flop_pos, "distance_tests_per_position": tests_pp,
+                     "pairs_in_cutoff_per_position": evals_pp,
+                     "note": "algorithmic flops only; masked lanes, the second Newton step, Philox and the Metropolis "
+                             "test are not counted"}
+    except Exception as e:  # the HBM roofline above is the contract; this one is an explanation
+        fp64_roof = {"error": str(e)}
+
     # DRAM bytes per launch of the sweep kernel from the newest committed `ncu --set full` capture
     import glob
     trs = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")))
@@ -427,7 +450,7 @@ def main():
                              "event pairs); slot arrays are %.0f MB per buffer"
                              % (info.ncol * info.ny * info.cell_capacity * 16 / 1e6)},
             "pair_evals_per_s": pair_rate, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "nselect2": nselect2,
+            "gpu_launches": int(launches), "clocks": clocks, "nselect2": nselect2, "roofline_fp64": fp64_roof,
             "acceptance": {"displacement": st["accepted"][0] / max(st["attempted"][0], 1),
                            "insertion": st["accepted"][1] / max(st["attempted"][1], 1),
                            "deletion": st["accepted"][2] / max(st["attempted"][2], 1)},

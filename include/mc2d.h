@@ -257,6 +257,10 @@ int mc2d_set_kernel_timing(mc2d_ctx *ctx, int on);
 int mc2d_get_stream(mc2d_ctx *ctx, void **stream_out);
 int mc2d_synchronize(mc2d_ctx *ctx);
 
+/* measured fp64 FMA throughput of the context's device in TFLOP/s (a short kernel of independent DFMA chains on
+ * every SM): the compute roofline bench.py reports next to the HBM one, which this path never approaches */
+int mc2d_measure_fp64_peak(mc2d_ctx *ctx, double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,7 +80,7 @@ EXPORTS = [
     "mc2d_calc_cell_ids", "mc2d_calc_neighbor_counts", "mc2d_calc_point_energies", "mc2d_run_sweep_traced",
     "mc2d_comm_unique_id", "mc2d_comm_init", "mc2d_allreduce_stats", "mc2d_get_info", "mc2d_get_stream",
     "mc2d_synchronize", "mc2d_set_kernel_timing", "mc2d_calc_neighbor_list", "mc2d_calc_energy_virial_bruteforce",
-    "mc2d_rescale_try", "mc2d_rescale_finish", "mc2d_probe_point", "mc2d_probe_particle", "mc2d_apply_probe",
+    "mc2d_rescale_try", "mc2d_rescale_finish", "mc2d_probe_point", "mc2d_probe_particle", "mc2d_apply_probe", "mc2d_measure_fp64_peak",
 ]
 
 _lib = None
@@ -136,6 +136,7 @@ def load_library() -> C.CDLL:
     L.mc2d_probe_point.argtypes = [vp, d, d, dp]
     L.mc2d_probe_particle.argtypes = [vp, ll, dp, dp, dp]
     L.mc2d_apply_probe.argtypes = [vp, i]
+    L.mc2d_measure_fp64_peak.argtypes = [vp, dp]
     _lib = L
     return L
 
@@ -433,6 +434,12 @@ class Context:
 
     def apply_probe(self, what: int):
         self._check(self.L.mc2d_apply_probe(self.h, what))
+
+    def measure_fp64_peak(self) -> float:
+        """measured fp64 FMA throughput of this device, TFLOP/s"""
+        t = C.c_double()
+        self._check(self.L.mc2d_measure_fp64_peak(self.h, C.byref(t)))
+        return t.value
 
     def set_kernel_timing(self, on: bool):
         self._check(self.L.mc2d_set_kernel_timing(self.h, int(on)))

@@ -1901,6 +1901,27 @@ extern "C" int mc2d_allreduce_stats(mc2d_ctx *ctx, mc2d_stats *st) {
 // ------------------------------------------------------------------------------------------------
 // introspection
 // ------------------------------------------------------------------------------------------------
+extern "C" int mc2d_measure_fp64_peak(mc2d_ctx *ctx, double *tflops) {
+    if (!ctx || !tflops) return MC2D_ERR_INVALID;
+    CU(cudaSetDevice(ctx->dev));
+    const int iters = 8192, blocks = ctx->num_sms * 8, threads = 256;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(ctx->ev0, ctx->stream));
+        k_fp64_peak<<<blocks, threads, 0, ctx->stream>>>(ctx->d_probe, iters, 0.999999, 1e-9);
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaGetLastError());
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+        if (rep > 0 && ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    ctx->launches += 4;
+    *tflops = best;
+    return MC2D_OK;
+}
+
 extern "C" int mc2d_get_info(mc2d_ctx *ctx, mc2d_info *o) {
     if (!ctx || !o) return MC2D_ERR_INVALID;
     const Grid &g = ctx->g;
