@@ -7,8 +7,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <map>
 #include <cub/cub.cuh>
 #include <string>
 #include <vector>
@@ -94,6 +96,25 @@ inline int even_up(int v, int m) { return ((v + m - 1) / m) * m; }
 
 }  // namespace
 
+// Small results come back through page-locked memory: a copy into pageable memory (a stack variable) makes the
+// driver stage and wait per copy, a pinned destination lets several copies share one stream synchronisation.
+// One named field per use, so nested helpers (count_particles inside fetch_stats ...) never alias.
+struct PinnedScalars {
+    int flags[4];
+    int errv[4];
+    int maxcount, ovf, csr_kept, pad;
+    unsigned long long kept, count, tn;
+    unsigned long long ps[2];
+    unsigned long long counters[8];
+    double uw[2];
+    double energy;
+};
+
+struct LaunchShape {
+    size_t smem = (size_t)-1;
+    int wpb = 0, occ = 0;
+};
+
 struct mc2d_ctx {
     mc2d_params prm;
     PairParams pp;
@@ -153,6 +174,8 @@ struct mc2d_ctx {
     double last_sweep_ms = 0, last_energy_ms = 0;
     long long last_tests = 0, last_evals = 0;
     unsigned long long attr_set = 0;  // bitmask of k_sweep instantiations whose smem attribute is set
+    PinnedScalars *hp = nullptr;  // cudaHostAlloc
+    std::map<const void *, LaunchShape> launch_shapes;  // per kernel: shape whose attribute / occupancy is cached
     long long n_last = 0;             // last known particle count (sizes the neighbour staging area)
     bool ktiming = false;
     std::vector<cudaEvent_t> kev;  // event pool for per-kernel timing
@@ -350,6 +373,8 @@ extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
     CU(cudaMalloc(&ctx->d_probe_sel, 2 * sizeof(int)));
     CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->dev));
     CU(cudaMalloc(&ctx->d_trace_n, sizeof(unsigned long long)));
+    CU(cudaHostAlloc(&ctx->hp, sizeof(PinnedScalars), cudaHostAllocDefault));
+    memset(ctx->hp, 0, sizeof(PinnedScalars));
     CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_energy, 0, 4 * sizeof(double), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
@@ -398,6 +423,7 @@ extern "C" int mc2d_destroy(mc2d_ctx *ctx) {
         if (ctx->d_probe) cudaFree(ctx->d_probe);
         if (ctx->d_probe_sel) cudaFree(ctx->d_probe_sel);
         if (ctx->d_trace_n) cudaFree(ctx->d_trace_n);
+        if (ctx->hp) cudaFreeHost(ctx->hp);
         if (ctx->ev0) cudaEventDestroy(ctx->ev0);
         if (ctx->ev1) cudaEventDestroy(ctx->ev1);
         if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
@@ -450,12 +476,12 @@ static int build_csr(mc2d_ctx *ctx, const double2 *d_xy, const int *d_ids, long 
     k_cell_bounds<<<(nn + 1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->keys_sorted.as<int>(), nn, ncell,
                                                                  ctx->start.as<int>());
     ctx->launches++;
-    int flags[4];
-    int kept = 0;
-    CU(cudaMemcpyAsync(flags, ctx->d_err, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&kept, ctx->start.as<int>() + ncell, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->hp->flags, ctx->d_err, sizeof ctx->hp->flags, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&ctx->hp->csr_kept, ctx->start.as<int>() + ncell, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
+    const int *flags = ctx->hp->flags;
+    const int kept = ctx->hp->csr_kept;
     if (flags[1] & 1) FAIL(MC2D_ERR_OUT_OF_BOX, "a position is NaN or outside [0,%g] x [0,%g]", ctx->prm.Lx, ctx->prm.Ly);
     if (n_kept) *n_kept = kept;
     return MC2D_OK;
@@ -718,30 +744,88 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
     }
     g.ox = g.oy = 0.0;
     const int ncell = g.ncs * g.ny;
+    const int cell0 = g.ghost * g.ny, nown = g.ncol * g.ny;
     long long kept = 0;
-    rc = build_csr(ctx, ctx->xy_in.as<double2>(), ids ? ctx->ids_in.as<int>() : nullptr, n, 1, g.nx, g.ny, g.dx, g.dy,
-                   ncell, &kept);
-    if (rc) return rc;
-    k_max_cell_count<<<(ncell + 255) / 256, 256, 0, ctx->stream>>>(ctx->start.as<int>(), ncell, ctx->d_err + 2);
-    ctx->launches++;
     int maxcount = 0;
-    CU(cudaMemcpyAsync(&maxcount, ctx->d_err + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (g.ghost && ctx->have_comm)  // every slab must use the same capacity: the halo copies whole slot columns
-        if ((rc = comm_max_int(ctx, &maxcount))) return rc;
-    int K = auto_capacity(ctx, maxcount);
-    if (K > 1024) FAIL(MC2D_ERR_CELL_OVERFLOW, "a cell holds %d particles; capacity %d exceeds the 1024-slot limit", maxcount, K);
-    if (K != ctx->allocK || (ctx->use_ids && !ctx->ids[0])) {
-        rc = alloc_slots(ctx, K);
-        if (rc) return rc;
+    // fault injection (tools/check_multi_gpu.py): odd ranks fall behind between the collective and their conversion
+    // kernel, so the neighbours' halo pushes land first
+    auto test_lag = [&]() {
+        if (const char *e = getenv("MC2D_TEST_UPLOAD_LAG_US"))
+            if ((ctx->prm.rank & 1) && atoi(e) > 0) usleep((useconds_t)atoi(e));
+    };
+    // Slot storage of a fitting capacity already exists (a re-upload): bin straight into the spare buffer, no sort.
+    // Every rank takes the same branch: allocK and use_ids are the same on all ranks, and so is the capacity
+    // computed from the global maximum below.
+    bool direct = ctx->arena && ctx->allocK > 0 && g.K == ctx->allocK && (!ctx->use_ids || ctx->ids[0]) &&
+                  !getenv("MC2D_UPLOAD_SORT");
+    const bool was_direct = direct;
+    if (direct) {
+        ctx->have_particles = false;  // the spare buffer may be the current one: a failed upload leaves nothing
+        const int K = g.K;
+        int *tag = ctx->use_ids ? ctx->ids[1] : nullptr;
+        if (!tag) {
+            CU(ctx->idx.ensure(sizeof(int) * (size_t)ncell * K));
+            tag = ctx->idx.as<int>();
+        }
+        CU(cudaMemsetAsync(ctx->cnt[1], 0, sizeof(int) * (size_t)ncell, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_pair_stats + 2, 0, sizeof(unsigned long long), ctx->stream));
+        if (n > 0) {
+            k_bin_direct<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+                ctx->xy_in.as<double2>(), (int)n, ctx->prm.Lx, ctx->prm.Ly, g, K, ctx->pos[1], ctx->cnt[1], tag,
+                ctx->d_err, ctx->d_pair_stats + 2);
+            ctx->launches++;
+        }
+        CU(cudaMemcpyAsync(ctx->hp->flags, ctx->d_err, sizeof ctx->hp->flags, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(&ctx->hp->kept, ctx->d_pair_stats + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaGetLastError());
+        const int *flags = ctx->hp->flags;
+        const unsigned long long nk = ctx->hp->kept;
+        if (flags[1] & 1) FAIL(MC2D_ERR_OUT_OF_BOX, "a position is NaN or outside [0,%g] x [0,%g]", ctx->prm.Lx, ctx->prm.Ly);
+        kept = (long long)nk;
+        maxcount = flags[2];
+        if (g.ghost && ctx->have_comm)
+            if ((rc = comm_max_int(ctx, &maxcount))) return rc;
+        test_lag();
+        if (auto_capacity(ctx, maxcount) != ctx->allocK) {
+            direct = false;  // the cells got fuller (or much emptier) than the storage was made for: sorted path
+        } else {
+            k_order_cells<<<(nown * 8 + 255) / 256, 256, 0, ctx->stream>>>(
+                ctx->pos[1], ctx->cnt[1], tag, ids ? ctx->ids_in.as<int>() : nullptr, cell0, nown, K, ctx->pos[0],
+                ctx->cnt[0], ctx->use_ids ? ctx->ids[0] : nullptr);
+            ctx->launches++;
+            ctx->cur = 0;
+        }
     }
-    ctx->cur = 0;
-    CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
-    k_csr_to_slots<<<(ncell + 7) / 8, 256, 0, ctx->stream>>>(ctx->spos.as<double2>(), ctx->sids.as<int>(),
-                                                             ctx->start.as<int>(), ncell, g.K, ctx->pos[0],
-                                                             ctx->cnt[0], ctx->use_ids ? ctx->ids[0] : nullptr,
-                                                             ctx->d_err);
-    ctx->launches++;
+    if (!direct) {
+        rc = build_csr(ctx, ctx->xy_in.as<double2>(), ids ? ctx->ids_in.as<int>() : nullptr, n, 1, g.nx, g.ny, g.dx, g.dy,
+                       ncell, &kept);
+        if (rc) return rc;
+        k_max_cell_count<<<(ncell + 255) / 256, 256, 0, ctx->stream>>>(ctx->start.as<int>(), ncell, ctx->d_err + 2);
+        ctx->launches++;
+        CU(cudaMemcpyAsync(&ctx->hp->maxcount, ctx->d_err + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        maxcount = ctx->hp->maxcount;
+        if (g.ghost && ctx->have_comm)  // every slab must use the same capacity: the halo copies whole slot columns
+            if ((rc = comm_max_int(ctx, &maxcount))) return rc;
+        int K = auto_capacity(ctx, maxcount);
+        if (K > 1024)
+            FAIL(MC2D_ERR_CELL_OVERFLOW, "a cell holds %d particles; capacity %d exceeds the 1024-slot limit", maxcount, K);
+        if (K != ctx->allocK || (ctx->use_ids && !ctx->ids[0])) {
+            rc = alloc_slots(ctx, K);
+            if (rc) return rc;
+        }
+        ctx->cur = 0;
+        if (!was_direct) test_lag();
+        CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
+        k_csr_to_slots<<<(nown + 7) / 8, 256, 0, ctx->stream>>>(ctx->spos.as<double2>(), ctx->sids.as<int>(),
+                                                                ctx->start.as<int>(), cell0, nown, g.K, ctx->pos[0],
+                                                                ctx->cnt[0], ctx->use_ids ? ctx->ids[0] : nullptr,
+                                                                ctx->d_err);
+        ctx->launches++;
+    }
     ctx->have_particles = true;
     ctx->rescale_pending = false;
     ctx->probe_pending = 0;
@@ -765,16 +849,22 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
     return MC2D_OK;
 }
 
-static int count_particles(mc2d_ctx *ctx, long long *n) {
+// enqueues the particle count of the owned cells; ctx->hp->count is valid after the next stream synchronisation
+static int count_particles_async(mc2d_ctx *ctx) {
     const Grid &g = ctx->g;
     const int cell0 = g.ghost * g.ny, ncell = g.ncol * g.ny;
     CU(cudaMemsetAsync(ctx->d_pair_stats + 2, 0, sizeof(unsigned long long), ctx->stream));
     k_sum_counts<<<(ncell + 255) / 256, 256, 0, ctx->stream>>>(ctx->cnt[ctx->cur], cell0, ncell, ctx->d_pair_stats + 2);
     ctx->launches++;
-    unsigned long long v = 0;
-    CU(cudaMemcpyAsync(&v, ctx->d_pair_stats + 2, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&ctx->hp->count, ctx->d_pair_stats + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    return MC2D_OK;
+}
+
+static int count_particles(mc2d_ctx *ctx, long long *n) {
+    if (int rc = count_particles_async(ctx)) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
-    *n = (long long)v;
+    *n = (long long)ctx->hp->count;
     ctx->n_last = *n;
     return MC2D_OK;
 }
@@ -875,10 +965,10 @@ static int build_order(mc2d_ctx *ctx) {
     const int ncell = g.ncol * g.ny;
     const size_t smem = sizeof(int) * (size_t)(3 * g.ny + g.ny / 2);
     if (smem > 200 * 1024) FAIL(MC2D_ERR_GEOMETRY, "grid has %d rows: too many for k_order_local", g.ny);
-    static bool attr = false;
-    if (smem > 40 * 1024 && !attr) {
+    LaunchShape &ls = ctx->launch_shapes[(const void *)k_order_local];
+    if (smem > 40 * 1024 && !ls.occ) {
         CU(cudaFuncSetAttribute(k_order_local, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
+        ls.occ = 1;
     }
     CU(ctx->order_buf.ensure(sizeof(int) * (size_t)ncell));
     k_order_local<<<dim3(g.ncol / 2, 4), ORDL_WARPS * 32, smem, ctx->stream>>>(g, ctx->cnt[ctx->cur], ctx->order_buf.as<int>());
@@ -922,19 +1012,18 @@ static int launch_energy_items(mc2d_ctx *ctx, double *U, double *W, bool *done) 
                 (int)lay.per_group, pU, pW, ctx->d_pair_stats, ctx->d_err);
         }
     });
-    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(pU, nblocks, 1.0, ctx->d_energy + 1, 0);
-    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(pW, nblocks, 1.0, ctx->d_energy + 2, 0);
+    k_reduce_partials<<<2, 1024, 0, ctx->stream>>>(pU, nblocks, 1.0, ctx->d_energy + 1, 0);  // U and W
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->launches += 3;
-    double uw[2];
-    unsigned long long ps[2];
-    int ovf = 0;
-    CU(cudaMemcpyAsync(uw, ctx->d_energy + 1, sizeof uw, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(ps, ctx->d_pair_stats, sizeof ps, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&ovf, ctx->d_err + 3, sizeof ovf, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->launches += 2;
+    PinnedScalars *hp = ctx->hp;
+    CU(cudaMemcpyAsync(hp->uw, ctx->d_energy + 1, sizeof hp->uw, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(hp->ps, ctx->d_pair_stats, sizeof hp->ps, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&hp->ovf, ctx->d_err + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
-    if (ovf) return MC2D_OK;
+    if (hp->ovf) return MC2D_OK;
+    const double *uw = hp->uw;
+    const unsigned long long *ps = hp->ps;
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_energy_ms = ms;
@@ -995,13 +1084,14 @@ static int energy_on_slots(mc2d_ctx *ctx, double *U, double *W, long long *N, bo
     const int half = (g.nx >= 3 && g.ny >= 3) ? 1 : 0;
     bool done = false;
     int rc = MC2D_OK;
+    // the particle count rides on the synchronisation of the energy launch
+    if ((rc = count_particles_async(ctx))) return rc;
     if (!getenv("MC2D_ENERGY_UNSTAGED")) rc = launch_energy_items(ctx, U, W, &done);
     if (rc) return rc;
     if (!done) rc = launch_energy(ctx, v, g.ncol * g.ny, half, false, nullptr, nullptr, U, W);
     if (rc) return rc;
-    long long n = 0;
-    rc = count_particles(ctx, &n);
-    if (rc) return rc;
+    long long n = (long long)ctx->hp->count;
+    ctx->n_last = n;
     if (resync) CU(cudaMemcpyAsync(ctx->d_energy, ctx->d_energy + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     if (allreduce && ctx->g.ghost) {
 #if MC2D_HAVE_NCCL_H
@@ -1378,16 +1468,18 @@ static int ktime_end(mc2d_ctx *ctx) {
 template <int POT, int G, bool TRACE>
 static int launch_sweep_p(mc2d_ctx *ctx, const SweepArgs &a, int wpb, size_t smem, int R, cudaStream_t stream,
                           int reserve_ctas) {
-    static size_t smem_seen = (size_t)-1;  // per instantiation: resident CTAs per SM for this launch shape
-    static int wpb_seen = 0, occ = 0;
-    if (smem != smem_seen || wpb != wpb_seen) {
+    // per context (= per device) and instantiation: resident CTAs per SM for this launch shape; the query costs
+    // tens of microseconds, so it is not repeated per launch
+    LaunchShape &ls = ctx->launch_shapes[(const void *)k_sweep_p<POT, G, TRACE>];
+    if (smem != ls.smem || wpb != ls.wpb) {
         CU(cudaFuncSetAttribute(k_sweep_p<POT, G, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         int nb = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sweep_p<POT, G, TRACE>, wpb * 32, smem));
-        occ = std::max(1, nb);
-        smem_seen = smem;
-        wpb_seen = wpb;
+        ls.occ = std::max(1, nb);
+        ls.smem = smem;
+        ls.wpb = wpb;
     }
+    const int occ = ls.occ;
     const int want = (a.nitems + wpb - 1) / wpb;
     // reserve_ctas: resident-CTA slots left free for the boundary kernel that runs next to this one
     const int grid = std::max(1, std::min(want, ctx->num_sms * occ - reserve_ctas));
@@ -1715,12 +1807,13 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(ctx->partial.as<double>(), 4 * nblocks, 1.0, ctx->d_energy, 1);
     ctx->launches++;
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
-    int errv[4];
-    CU(cudaMemcpyAsync(errv, ctx->d_err, sizeof errv, cudaMemcpyDeviceToHost, ctx->stream));
-    unsigned long long tn = 0;
-    if (trace) CU(cudaMemcpyAsync(&tn, ctx->d_trace_n, sizeof tn, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->hp->errv, ctx->d_err, sizeof ctx->hp->errv, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->hp->tn = 0;
+    if (trace) CU(cudaMemcpyAsync(&ctx->hp->tn, ctx->d_trace_n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
+    const int *errv = ctx->hp->errv;
+    const unsigned long long tn = ctx->hp->tn;
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_sweep_ms = ms;
@@ -1756,13 +1849,13 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
 }
 
 static int fetch_stats(mc2d_ctx *ctx, mc2d_stats *st) {
-    unsigned long long c[8];
-    double e = 0;
-    CU(cudaMemcpyAsync(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&e, ctx->d_energy, sizeof e, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->hp->counters, ctx->d_counters, sizeof ctx->hp->counters, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&ctx->hp->energy, ctx->d_energy, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     long long n = 0;
-    int rc = count_particles(ctx, &n);
+    int rc = count_particles(ctx, &n);  // synchronises the stream
     if (rc) return rc;
+    const unsigned long long *c = ctx->hp->counters;
+    const double e = ctx->hp->energy;
     for (int i = 0; i < 3; ++i) {
         st->attempted[i] = (long long)c[i];
         st->accepted[i] = (long long)c[3 + i];

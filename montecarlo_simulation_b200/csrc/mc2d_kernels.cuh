@@ -267,10 +267,13 @@ __global__ void __launch_bounds__(256) k_energy_virial(V v, PairParams pp, doubl
     }
 }
 
-// fixed-order final reduction of per-CTA partials: out[0] += / = scale * sum(part[0..n))
+// fixed-order final reduction of per-CTA partials: out[b] += / = scale * sum(part[b*n .. b*n + n)) for CTA b
+// (one CTA per quantity: U and W of a reduction lie behind each other)
 __global__ void __launch_bounds__(1024) k_reduce_partials(const double *part, int n, double scale, double *out,
                                                           int accumulate) {
     __shared__ double red[32];
+    part += (size_t)blockIdx.x * n;
+    out += blockIdx.x;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // 4 independent chains: loads overlap
     int i = threadIdx.x;
     const int st = blockDim.x;
@@ -481,11 +484,14 @@ __global__ void k_max_cell_count(const int *start, int ncell, int *out_max) {
 }
 
 // CSR (keys = stored cell index) -> slot layout.  One warp per stored cell.
-__global__ void k_csr_to_slots(const double2 *spos, const int *sids, const int *start, int ncell_store, int K,
+// Only the owned cells [cell0, cell0 + ncell) are written: a ghost column belongs to the neighbour, who may
+// already be pushing into it (k_halo_sync) while this rank is still converting.
+__global__ void k_csr_to_slots(const double2 *spos, const int *sids, const int *start, int cell0, int ncell, int K,
                                double2 *pos, int *cnt, int *ids, int *err) {
     const int lane = threadIdx.x & 31;
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= ncell_store) return;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= ncell) return;
+    const int c = cell0 + w;
     const int b = start[c], n = start[c + 1] - b;
     if (n > K) {
         if (lane == 0) atomicMax(&err[0], n);
@@ -496,6 +502,71 @@ __global__ void k_csr_to_slots(const double2 *spos, const int *sids, const int *
         if (ids) ids[(size_t)c * K + s] = sids[b + s];
     }
     if (lane == 0) cnt[c] = n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1, second and later uploads into slot storage that already exists (the end-to-end pattern: upload,
+// sweep, download, upload ...): no key sort.  k_bin_direct drops every particle into a slot of its cell
+// in the SPARE buffer (slot = atomicAdd on the cell count, so the order inside a cell is arbitrary) and
+// remembers its input index; k_order_cells copies each owned cell into buffer 0 by ascending input index,
+// which is the order the stable key sort gives: the slot arrays are bit-identical to the sorted path's.
+// flags = ctx->d_err: [1] bit 0 = a position outside the box, [2] = largest cell count seen.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bin_direct(const double2 *xy, int n, double Lx, double Ly, Grid g, int K,
+                                                    double2 *pos, int *cnt, int *tag, int *flags,
+                                                    unsigned long long *kept) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool own = false, bad = false;
+    int seen = 0;
+    if (i < n) {
+        const double2 p = xy[i];
+        bad = !(p.x >= 0.0 && p.x <= Lx && p.y >= 0.0 && p.y <= Ly);
+        int gcx, cy;
+        sweep_cell_of(g, p.x, p.y, gcx, cy);
+        const int lc = wrap_index(gcx - g.col0, g.nx);
+        own = !bad && lc < g.ncol;
+        if (own) {
+            const int c = (lc + g.ghost) * g.ny + cy;
+            const int s = atomicAdd(&cnt[c], 1);
+            seen = s + 1;
+            if (s < K) {
+                pos[(size_t)c * K + s] = p;
+                tag[(size_t)c * K + s] = i;
+            }
+        }
+    }
+    if (__any_sync(FULL_MASK, bad) && lane == 0) atomicOr(&flags[1], 1);
+    const unsigned m = __ballot_sync(FULL_MASK, own);
+    seen = max(seen, __shfl_xor_sync(FULL_MASK, seen, 16));
+    seen = max(seen, __shfl_xor_sync(FULL_MASK, seen, 8));
+    seen = max(seen, __shfl_xor_sync(FULL_MASK, seen, 4));
+    seen = max(seen, __shfl_xor_sync(FULL_MASK, seen, 2));
+    seen = max(seen, __shfl_xor_sync(FULL_MASK, seen, 1));
+    if (lane == 0 && m) {
+        atomicMax(&flags[2], seen);
+        atomicAdd(kept, (unsigned long long)__popc(m));
+    }
+}
+
+// 8 lanes per owned cell; rank of a particle = number of particles of the cell with a smaller input index
+__global__ void __launch_bounds__(256) k_order_cells(const double2 *pos_s, const int *cnt_s, const int *tag,
+                                                     const int *ids_in, int cell0, int ncell, int K, double2 *pos,
+                                                     int *cnt, int *ids) {
+    constexpr int G = 8;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) / G, sl = threadIdx.x % G;
+    if (w >= ncell) return;
+    const int c = cell0 + w;
+    const int n = min(cnt_s[c], K);
+    const size_t base = (size_t)c * K;
+    for (int s = sl; s < n; s += G) {
+        const int t = tag[base + s];
+        int r = 0;
+        for (int j = 0; j < n; ++j) r += tag[base + j] < t;
+        pos[base + r] = pos_s[base + s];
+        if (ids) ids[base + r] = ids_in ? ids_in[t] : t;
+    }
+    if (sl == 0) cnt[c] = n;
 }
 
 // ---------------------------------------------------------------------------------------------

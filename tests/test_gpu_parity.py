@@ -260,6 +260,73 @@ def test_upload_download_roundtrip_and_slot_energy(mc, oracle, Lx, Ly, nx, ny):
         assert relerr(ctx.stats()["energy"], U) < 1e-15  # initial running energy (MC.cpp:26)
 
 
+@pytest.mark.parametrize("with_ids", [True, False])
+def test_reupload_without_sort_gives_identical_slots(mc, monkeypatch, with_ids):
+    """A second upload into existing slot storage bins directly (k_bin_direct + k_order_cells, no key sort).  The slot
+    arrays must be bit-identical to the sorted path's: same download order, same ids, same trajectory afterwards."""
+    Lx = Ly = 61.0
+    rng = np.random.default_rng(5)
+    xy = lattice(48, 40, Lx, Ly, 0.3, 7)
+    xy = xy[rng.permutation(len(xy))]  # input order unrelated to the cells
+    ids = (np.arange(len(xy), dtype=np.int32) * 7 + 3) if with_ids else None
+
+    def run(reuploads, sort_only):
+        if sort_only:
+            monkeypatch.setenv("MC2D_UPLOAD_SORT", "1")
+        else:
+            monkeypatch.delenv("MC2D_UPLOAD_SORT", raising=False)
+        with mc.Context(Lx, Ly, 2.5, T=1.0, activity=0.3, delta=0.15, seed=11) as ctx:
+            ctx.upload(xy, ids)
+            first = ctx.info().launches
+            for _ in range(reuploads):
+                before = ctx.info().launches
+                ctx.upload(xy, ids)
+                again = ctx.info().launches - before
+            U0 = ctx.total_energy_virial()[0]
+            d0 = ctx.download(with_ids=with_ids)
+            st = ctx.run_sweeps(3, gc_per_cell=1)
+            d1 = ctx.download(with_ids=with_ids)
+            return first, (again if reuploads else None), U0, d0, st, d1
+
+    first, again, U0, d0, st, d1 = run(2, False)
+    assert again < first - 4  # the sort, gather and offset kernels did not run
+    for ref in (run(0, False), run(2, True)):
+        if ref[1] is not None:
+            assert ref[1] >= first - 1  # MC2D_UPLOAD_SORT=1: the sorted path again
+        assert U0 == ref[2]
+        if with_ids:
+            assert (d0[0] == ref[3][0]).all() and (d0[1] == ref[3][1]).all()
+            assert d1[0].shape == ref[5][0].shape and (d1[0] == ref[5][0]).all() and (d1[1] == ref[5][1]).all()
+        else:
+            assert (d0 == ref[3]).all()
+            assert d1.shape == ref[5].shape and (d1 == ref[5]).all()
+        assert st["accepted"] == ref[4]["accepted"] and st["energy"] == ref[4]["energy"]
+
+
+def test_reupload_of_a_denser_configuration_falls_back_to_the_sort(mc, oracle):
+    """storage made for a dilute system, then a configuration whose cells need more slots: the direct path notices
+    (largest cell count) and the sorted path re-allocates."""
+    Lx = Ly = 40.0
+    calc = oracle.calc(1.0, 0.0, ol.LJ, 2.5)
+    dilute = lattice(16, 16, Lx, Ly, 0.2, 3)
+    dense = lattice(44, 44, Lx, Ly, 0.02, 4)
+    with mc.Context(Lx, Ly, 2.5) as ctx:
+        ctx.upload(dilute)
+        k0 = ctx.info().cell_capacity
+        ctx.upload(dense)
+        assert ctx.info().cell_capacity >= k0 and ctx.num_particles() == len(dense)
+        assert relerr(ctx.total_energy_virial()[0], oracle.total_energy_celllist(calc, Lx, Ly, dense)) < REL
+        ctx.upload(dilute)
+        assert ctx.num_particles() == len(dilute)
+        assert relerr(ctx.total_energy_virial()[0], oracle.total_energy_celllist(calc, Lx, Ly, dilute)) < REL
+        with pytest.raises(mc.MC2DError):
+            ctx.upload(np.array([[1.0, 1.0], [Lx + 5.0, 3.0]]))
+        with pytest.raises(mc.MC2DError):  # a failed direct upload leaves no configuration behind
+            ctx.total_energy_virial()
+        ctx.upload(dilute)
+        assert ctx.num_particles() == len(dilute)
+
+
 # ---- the step loop -----------------------------------------------------------------------------------------------------
 
 def test_nvt_sweeps_conserve_and_track_energy(mc, oracle):

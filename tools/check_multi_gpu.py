@@ -49,6 +49,16 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(ids[0])
         ctx.upload(xy)  # every rank passes the full set; the library keeps its slab
+        # Re-uploads into live storage (the end-to-end pattern) with the odd ranks held back after the collective:
+        # the neighbours' ghost pushes land before the late rank converts its own cells, which must leave the
+        # ghost columns alone.  NVT pass: direct binning; GCMC pass: the sorted path.
+        os.environ["MC2D_TEST_UPLOAD_LAG_US"] = "3000"
+        if label == "GCMC":
+            os.environ["MC2D_UPLOAD_SORT"] = "1"
+        for _ in range(3):
+            ctx.upload(xy)
+        os.environ.pop("MC2D_TEST_UPLOAD_LAG_US")
+        os.environ.pop("MC2D_UPLOAD_SORT", None)
         U0, W0, N0 = ctx.total_energy_virial(allreduce=True)
         st = ctx.run_sweeps(25, **plan)
         st_all = ctx.allreduce_stats(st)
