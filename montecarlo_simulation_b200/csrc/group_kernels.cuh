@@ -324,14 +324,13 @@ __global__ void __launch_bounds__(256) k_energy_p(const double2 *pos, const int 
                                                   double *partU, double *partW, unsigned long long *pair_stats,
                                                   int *err) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double red[32];
     constexpr int GPW = 32 / G;
     const int K = g.K;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int gi = lane / G, sl = lane % G;
     double2 *cand = reinterpret_cast<double2 *>(smem_raw + (size_t)(wib * GPW + gi) * stride);
     const int nay = g.ny >> 1, npairs = g.ncol >> 1;
-    const int idx = blockIdx.x * wpb + wib;  // heavy-first over (item, colour)
+    const int idx = blockIdx.x * wpb + wib;  // heavy-first over (item, colour); also the index of the warp's partial sums
     const int colour = idx & 3, item = idx >> 2;
     const int px = colour & 1, py = colour >> 1;
     const double hLx = 0.5 * g.Lx, hLy = 0.5 * g.Ly;
@@ -362,32 +361,32 @@ __global__ void __launch_bounds__(256) k_energy_p(const double2 *pos, const int 
     }
     const bool work = n_own > 0 && POT != POT_IDEAL;
     const double x_lo = g.ox + gcx * g.dx, y_lo = g.oy + cy * g.dy;
-    if (work) {
-        for (int s = sl; s < n_own; s += G) cp_async16(&cand[Mf + s], &pos[(size_t)(col3[1] + row3[1]) * K + s]);
-        int pre = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if ((q % G) == sl)
-                for (int s = 0; s < nf[q]; ++s) cp_async16(&cand[pre + s], &pos[(size_t)cf[q] * K + s]);
-            pre += nf[q];
+    const int ntot = work ? Mf + n_own : 0;
+    {
+        // candidate k of the group: forward neighbours in the order (0,+1), (+1,-1), (+1,0), (+1,+1), then the own
+        // cell; one cp.async per lane and round
+        const int t1 = nf[0], t2 = t1 + nf[1], t3 = t2 + nf[2];
+        const int own = col3[1] + row3[1];
+        for (int k = sl; k < ntot; k += G) {
+            const int q = (k >= t1) + (k >= t2) + (k >= t3) + (k >= Mf);
+            const int cell = q == 0 ? cf[0] : (q == 1 ? cf[1] : (q == 2 ? cf[2] : (q == 3 ? cf[3] : own)));
+            const int first = q == 0 ? 0 : (q == 1 ? t1 : (q == 2 ? t2 : (q == 3 ? t3 : Mf)));
+            cp_async16(&cand[k], &pos[(size_t)cell * K + (k - first)]);
         }
     }
     cp_async_wait_all();
     __syncwarp();
-    const int ntot = work ? Mf + n_own : 0;
-    const int KM = warp_max_int(ntot), N0 = warp_max_int(work ? n_own : 0);
-    const double2 far2 = make_double2(MC2D_FAR, MC2D_FAR);
     for (int k = sl; k < ntot; k += G) cand[k] = to_local(cand[k], x_lo, y_lo, g, hLx, hLy);
-    for (int k = ntot + sl; k < min(KM, cap); k += G) cand[k] = far2;
     __syncwarp();
 
+    // Per-group loop bounds: the groups of a warp diverge on the trip counts only (equally full cells share a warp,
+    // k_order_local), there is no shuffle inside the loops.
     double a = 0.0, b = 0.0, accU = 0.0, accW = 0.0;
     unsigned int evals = 0;
-    for (int i = 0; i < N0; ++i) {
-        // an idle group probes from the opposite far corner: every distance is ~2e150, beyond the cutoff
-        const double2 ui = (i < n_own) ? cand[Mf + i] : make_double2(-MC2D_FAR, -MC2D_FAR);
+    for (int i = 0; i < (work ? n_own : 0); ++i) {
+        const double2 ui = cand[Mf + i];
         const int first_own = Mf + i;  // own candidates count from j > i
-        for (int k = sl; k < KM; k += G) {
+        for (int k = sl; k < ntot; k += G) {
             const double2 c = cand[k];
             const double dx = c.x - ui.x, dy = c.y - ui.y;
             const double r2 = fma(dx, dx, dy * dy);
@@ -408,15 +407,16 @@ __global__ void __launch_bounds__(256) k_energy_p(const double2 *pos, const int 
             evals += ok;
         }
     }
+    __syncwarp();
     if (POT == POT_LJ || POT == POT_WCA) {
         accU = 4.0 * (a - b) + (POT == POT_WCA ? (double)evals : 0.0);
         accW = 48.0 * a - 24.0 * b;
     }
-    const double sU = block_sum(accU, red);
-    const double sW = block_sum(accW, red);
-    if (threadIdx.x == 0) {
-        partU[blockIdx.x] = sU;
-        partW[blockIdx.x] = sW;
+    // one partial per warp (fixed order inside the warp, fixed-order final reduction): no block barrier
+    const double sU = warp_sum(accU), sW = warp_sum(accW);
+    if (lane == 0) {
+        partU[idx] = sU;
+        partW[idx] = sW;
     }
     // distance tests of this cell: n * Mf forward pairs + n (n - 1) / 2 own pairs
     const unsigned int tests_g = (sl == 0 && work) ? (unsigned int)(n_own * Mf + n_own * (n_own - 1) / 2) : 0u;

@@ -994,8 +994,9 @@ static int launch_energy_items(mc2d_ctx *ctx, double *U, double *W, bool *done) 
     const int nblocks = (4 * nitems + wpb - 1) / wpb;
     const size_t smem = lay.per_group * (32 / G) * wpb;
     const int cap = lay.nb_cap + g.K;
-    CU(ctx->partial.ensure(sizeof(double) * 2 * (size_t)nblocks));
-    double *pU = ctx->partial.as<double>(), *pW = pU + nblocks;
+    const int nparts = nblocks * wpb;  // one partial sum per warp
+    CU(ctx->partial.ensure(sizeof(double) * 2 * (size_t)nparts));
+    double *pU = ctx->partial.as<double>(), *pW = pU + nparts;
     CU(cudaMemsetAsync(ctx->d_pair_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_err + 3, 0, sizeof(int), ctx->stream));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -1012,7 +1013,7 @@ static int launch_energy_items(mc2d_ctx *ctx, double *U, double *W, bool *done) 
                 (int)lay.per_group, pU, pW, ctx->d_pair_stats, ctx->d_err);
         }
     });
-    k_reduce_partials<<<2, 1024, 0, ctx->stream>>>(pU, nblocks, 1.0, ctx->d_energy + 1, 0);  // U and W
+    k_reduce_partials<<<2, 1024, 0, ctx->stream>>>(pU, nparts, 1.0, ctx->d_energy + 1, 0);  // U and W
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 2;
     PinnedScalars *hp = ctx->hp;
