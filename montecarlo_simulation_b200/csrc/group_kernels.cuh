@@ -365,13 +365,17 @@ __global__ void __launch_bounds__(256) k_energy_p(const double2 *pos, const int 
     {
         // candidate k of the group: forward neighbours in the order (0,+1), (+1,-1), (+1,0), (+1,+1), then the own
         // cell; one cp.async per lane and round
+        // (slot index of candidate k) = k + o_q for the cell q it lies in: 32-bit offsets, picked by running compares
         const int t1 = nf[0], t2 = t1 + nf[1], t3 = t2 + nf[2];
-        const int own = col3[1] + row3[1];
+        const int o0 = cf[0] * K, o1 = cf[1] * K - t1, o2 = cf[2] * K - t2, o3 = cf[3] * K - t3,
+                  o4 = (col3[1] + row3[1]) * K - Mf;
         for (int k = sl; k < ntot; k += G) {
-            const int q = (k >= t1) + (k >= t2) + (k >= t3) + (k >= Mf);
-            const int cell = q == 0 ? cf[0] : (q == 1 ? cf[1] : (q == 2 ? cf[2] : (q == 3 ? cf[3] : own)));
-            const int first = q == 0 ? 0 : (q == 1 ? t1 : (q == 2 ? t2 : (q == 3 ? t3 : Mf)));
-            cp_async16(&cand[k], &pos[(size_t)cell * K + (k - first)]);
+            int o = o0;
+            o = k >= t1 ? o1 : o;
+            o = k >= t2 ? o2 : o;
+            o = k >= t3 ? o3 : o;
+            o = k >= Mf ? o4 : o;
+            cp_async16(&cand[k], &pos[o + k]);
         }
     }
     cp_async_wait_all();

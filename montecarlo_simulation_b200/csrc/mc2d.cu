@@ -442,8 +442,10 @@ extern "C" int mc2d_destroy(mc2d_ctx *ctx) {
 // mode 0: reference grid (nx,ny,cdx,cdy given); mode 1: checkerboard grid ctx->g, slab filter.
 // On return ctx->spos / ctx->sids (perm or ids) / ctx->start hold the CSR arrays; *n_kept = number of
 // particles with a real (non-sentinel) key.
+// bad_out != nullptr: a position outside the box is reported there instead of failing (mc2d_upload lets all
+// ranks agree on the failure before any of them returns).
 static int build_csr(mc2d_ctx *ctx, const double2 *d_xy, const int *d_ids, long long n, int mode, int nx, int ny,
-                     double cdx, double cdy, int ncell, long long *n_kept) {
+                     double cdx, double cdy, int ncell, long long *n_kept, bool *bad_out = nullptr) {
     const int nn = (int)n;
     CU(ctx->keys.ensure(sizeof(int) * (size_t)(nn + 1)));
     CU(ctx->keys_sorted.ensure(sizeof(int) * (size_t)(nn + 1)));
@@ -482,7 +484,10 @@ static int build_csr(mc2d_ctx *ctx, const double2 *d_xy, const int *d_ids, long 
     CU(cudaGetLastError());
     const int *flags = ctx->hp->flags;
     const int kept = ctx->hp->csr_kept;
-    if (flags[1] & 1) FAIL(MC2D_ERR_OUT_OF_BOX, "a position is NaN or outside [0,%g] x [0,%g]", ctx->prm.Lx, ctx->prm.Ly);
+    if (bad_out)
+        *bad_out = (flags[1] & 1) != 0;
+    else if (flags[1] & 1)
+        FAIL(MC2D_ERR_OUT_OF_BOX, "a position is NaN or outside [0,%g] x [0,%g]", ctx->prm.Lx, ctx->prm.Ly);
     if (n_kept) *n_kept = kept;
     return MC2D_OK;
 }
@@ -661,6 +666,8 @@ static int alloc_slots(mc2d_ctx *ctx, int K) {
         if (int rc = comm_barrier(ctx)) return rc;
     free_slots(ctx);
     const size_t ncell = (size_t)ctx->g.ncs * ctx->g.ny;
+    if (ncell * (size_t)K >= 0x7fffffffULL)  // kernels index slots with 32-bit integers
+        FAIL(MC2D_ERR_GEOMETRY, "%zu cells x %d slots do not fit a 32-bit slot index; use more ranks", ncell, K);
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
     size_t off = 256;  // [0] flag from left, [1] flag from right, [2] CTA ticket of k_halo_sync
     for (int b = 0; b < 2; ++b) {
@@ -749,6 +756,8 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
     int maxcount = 0;
     // fault injection (tools/check_multi_gpu.py): odd ranks fall behind between the collective and their conversion
     // kernel, so the neighbours' halo pushes land first
+    // A bad position on one rank fails the upload on every rank: the flag travels with the collective maximum.
+    constexpr int kOutOfBox = 0x7fffffff;
     auto test_lag = [&]() {
         if (const char *e = getenv("MC2D_TEST_UPLOAD_LAG_US"))
             if ((ctx->prm.rank & 1) && atoi(e) > 0) usleep((useconds_t)atoi(e));
@@ -783,11 +792,12 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
         CU(cudaGetLastError());
         const int *flags = ctx->hp->flags;
         const unsigned long long nk = ctx->hp->kept;
-        if (flags[1] & 1) FAIL(MC2D_ERR_OUT_OF_BOX, "a position is NaN or outside [0,%g] x [0,%g]", ctx->prm.Lx, ctx->prm.Ly);
         kept = (long long)nk;
-        maxcount = flags[2];
+        maxcount = (flags[1] & 1) ? kOutOfBox : flags[2];
         if (g.ghost && ctx->have_comm)
             if ((rc = comm_max_int(ctx, &maxcount))) return rc;
+        if (maxcount == kOutOfBox)
+            FAIL(MC2D_ERR_OUT_OF_BOX, "a position is NaN or outside [0,%g] x [0,%g]", ctx->prm.Lx, ctx->prm.Ly);
         test_lag();
         if (auto_capacity(ctx, maxcount) != ctx->allocK) {
             direct = false;  // the cells got fuller (or much emptier) than the storage was made for: sorted path
@@ -800,16 +810,19 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
         }
     }
     if (!direct) {
+        bool bad = false;
         rc = build_csr(ctx, ctx->xy_in.as<double2>(), ids ? ctx->ids_in.as<int>() : nullptr, n, 1, g.nx, g.ny, g.dx, g.dy,
-                       ncell, &kept);
+                       ncell, &kept, &bad);
         if (rc) return rc;
         k_max_cell_count<<<(ncell + 255) / 256, 256, 0, ctx->stream>>>(ctx->start.as<int>(), ncell, ctx->d_err + 2);
         ctx->launches++;
         CU(cudaMemcpyAsync(&ctx->hp->maxcount, ctx->d_err + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        maxcount = ctx->hp->maxcount;
+        maxcount = bad ? kOutOfBox : ctx->hp->maxcount;
         if (g.ghost && ctx->have_comm)  // every slab must use the same capacity: the halo copies whole slot columns
             if ((rc = comm_max_int(ctx, &maxcount))) return rc;
+        if (maxcount == kOutOfBox)
+            FAIL(MC2D_ERR_OUT_OF_BOX, "a position is NaN or outside [0,%g] x [0,%g]", ctx->prm.Lx, ctx->prm.Ly);
         int K = auto_capacity(ctx, maxcount);
         if (K > 1024)
             FAIL(MC2D_ERR_CELL_OVERFLOW, "a cell holds %d particles; capacity %d exceeds the 1024-slot limit", maxcount, K);

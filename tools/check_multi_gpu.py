@@ -86,6 +86,30 @@ def main():
                   % (label, world, same_pos, same_cnt, N1, n1, U1, u1, st_all["energy"], s1["energy"],
                      "OK" if good else "MISMATCH"), flush=True)
             ok = ok and good
+    # a position outside the box on ONE rank must fail the upload on EVERY rank (no rank left waiting in a collective)
+    ctx = m.Context(L, L, 2.5, T=1.0, delta=0.1, seed=11, device=local, rank=rank, nranks=world)
+    ids = [api.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.comm_init(ids[0])
+    for attempt in range(2):  # first upload: sorted path; second: direct binning
+        bad = xy.copy()
+        if rank == world - 1:
+            bad[5, 0] = L + 1.0
+        try:
+            ctx.upload(bad if attempt == 1 else xy)
+            raised = False
+        except m.MC2DError as e:
+            raised = e.status == 6
+        want = attempt == 1
+        if raised != want:
+            print("rank %d: upload attempt %d raised=%s, expected %s" % (rank, attempt, raised, want), flush=True)
+            ok = False
+    ctx.close()
+    bad_any = torch.tensor([0 if (ok or rank == 0) else 1], device="cuda")
+    dist.all_reduce(bad_any)
+    if rank == 0:
+        ok = ok and int(bad_any.item()) == 0
+        print("out-of-box on one rank fails everywhere -> %s" % ("OK" if int(bad_any.item()) == 0 else "MISMATCH"), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()
