@@ -911,7 +911,7 @@ extern "C" int mc2d_download(mc2d_ctx *ctx, double *xy, int *ids, long long cap,
     if (n == 0) return MC2D_OK;
     CU(ctx->spos.ensure(sizeof(double2) * (size_t)n));
     CU(ctx->sids.ensure(sizeof(int) * (size_t)n));
-    k_compact<<<(ncell + 7) / 8, 256, 0, ctx->stream>>>(ctx->pos[ctx->cur], ctx->cnt[ctx->cur],
+    k_compact<<<(ncell * 4 + 255) / 256, 256, 0, ctx->stream>>>(ctx->pos[ctx->cur], ctx->cnt[ctx->cur],
                                                         ctx->use_ids ? ctx->ids[ctx->cur] : nullptr,
                                                         ctx->offsets.as<int>(), cell0, ncell, g.K,
                                                         ctx->spos.as<double2>(), ids ? ctx->sids.as<int>() : nullptr);

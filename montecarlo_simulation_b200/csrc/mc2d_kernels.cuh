@@ -650,13 +650,15 @@ __global__ void __launch_bounds__(256) k_rebin(const double2 *pos_o, const int *
 }
 
 // slot layout -> compact array (download).  offsets = exclusive scan of the owned cells' counts.
+// 4 lanes per cell (a cell holds ~3 particles): the count and offset loads of a warp are 8 consecutive words.
 __global__ void k_compact(const double2 *pos, const int *cnt, const int *ids, const int *offsets, int cell0,
                           int ncell, int K, double2 *out, int *ids_out) {
-    const int lane = threadIdx.x & 31;
-    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    constexpr int G = 4;
+    const int lane = threadIdx.x % G;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     if (w >= ncell) return;
     const int c = cell0 + w, n = cnt[c], o = offsets[w];
-    for (int s = lane; s < n; s += 32) {
+    for (int s = lane; s < n; s += G) {
         out[o + s] = pos[(size_t)c * K + s];
         if (ids_out) ids_out[o + s] = ids ? ids[(size_t)c * K + s] : -1;
     }

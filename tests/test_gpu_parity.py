@@ -325,6 +325,10 @@ def test_reupload_of_a_denser_configuration_falls_back_to_the_sort(mc, oracle):
             ctx.total_energy_virial()
         ctx.upload(dilute)
         assert ctx.num_particles() == len(dilute)
+        ctx.upload(np.zeros((0, 2)))  # an empty re-upload
+        assert ctx.num_particles() == 0 and ctx.total_energy_virial()[0] == 0.0
+        ctx.upload(dilute[:1])
+        assert ctx.num_particles() == 1 and (ctx.download() == dilute[:1]).all()
 
 
 # ---- the step loop -----------------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Short driver for ncu: config #4 (1M particles, GCMC LJ), a few sweeps + one energy reduction.
+"""Short driver for ncu: config #4 (1M particles, GCMC LJ): upload, a few sweeps, one energy reduction, download
+and a re-upload (the end-to-end pattern; the second upload takes the sort-free path).
 Usage: python tools/profile_step.py [sweeps]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,4 +14,6 @@ with m.Context(wl["L"], wl["L"], bench.RCUT, T=bench.T_BENCH, activity=bench.Z_L
     ctx.upload(wl["xy"])
     st = ctx.run_sweeps(sweeps, disp_per_particle=1, gc_per_cell=1, disp_per_cell=dpc)
     U, W, N = ctx.total_energy_virial(resync=True)
+    xy = ctx.download()
+    ctx.upload(xy)
     print("N=%d U=%.6f moves=%d sweep_ms=%.3f energy_ms=%.3f" % (N, U, sum(st["attempted"]), ctx.info().last_sweep_ms, ctx.info().last_energy_ms))

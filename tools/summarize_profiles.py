@@ -48,6 +48,10 @@ def short(name):
     return re.sub(r"\(.*", "", name)[:70]
 
 
+LAUNCH_CMD = "python tools/profile_step.py 3` (config #4, 1M particles, upload + 3 GCMC sweeps + 1 energy/virial)"
+FULL_CMD = "python tools/profile_step.py 3"
+
+
 def launches(tag, path):
     shutil.copy(path, os.path.join(PROF, "%s_launches.csv" % tag))
     lines = [l for l in open(path) if not l.startswith("==")]
@@ -59,9 +63,8 @@ def launches(tag, path):
         agg.setdefault(short(row["Kernel Name"]), []).append(v)
     tot = sum(sum(v) for v in agg.values())
     with open(os.path.join(PROF, "%s_launches.md" % tag), "w") as fh:
-        fh.write("# %s — launch list of `python tools/profile_step.py 3` (config #4, 1M particles, upload + 3 GCMC "
-                 "sweeps + 1 energy/virial)\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` — "
-                 "cold-cache, serialised: compare SHARES, not absolutes.\n\n" % tag)
+        fh.write("# %s — launch list of `%s\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` — "
+                 "cold-cache, serialised: compare SHARES, not absolutes.\n\n" % (tag, LAUNCH_CMD))
         fh.write("| kernel | launches | avg µs | sum µs | share |\n|---|---:|---:|---:|---:|\n")
         for k, v in agg.items():
             fh.write("| `%s` | %d | %.1f | %.1f | %.1f%% |\n" % (k, len(v), sum(v) / len(v) / 1e3, sum(v) / 1e3,
@@ -84,8 +87,8 @@ def ncu_summary(tag, rep):
     traffic = {}
     with open(os.path.join(PROF, "%s_ncu_summary.md" % tag), "w") as fh:
         fh.write("# %s — `ncu --set full --clock-control none --import-source on`, one launch per kernel\n\n"
-                 "Command: `python tools/profile_step.py 3` (config #4: 1M particles, GCMC LJ). ncu flushes caches "
-                 "between replays, so DRAM bytes are cold-cache figures.\n\n" % tag)
+                 "Command: `%s` (config #4: 1M particles, GCMC LJ). ncu flushes caches "
+                 "between replays, so DRAM bytes are cold-cache figures.\n\n" % (tag, FULL_CMD))
         for k, r in seen.items():
             fh.write("## `%s`\n\n| metric | value |\n|---|---|\n" % k)
             for m, label in METRICS:
@@ -106,6 +109,10 @@ def ncu_summary(tag, rep):
 
 if __name__ == "__main__":
     tag, lcsv, rep = sys.argv[1:4]
+    if len(sys.argv) > 4:  # what was run for the launch list / for the full capture
+        LAUNCH_CMD = sys.argv[4]
+    if len(sys.argv) > 5:
+        FULL_CMD = sys.argv[5]
     os.makedirs(PROF, exist_ok=True)
     launches(tag, lcsv)
     ncu_summary(tag, rep)
