@@ -386,6 +386,7 @@ def main():
     ctx.upload(host[:n_host])  # one untimed round trip (first-touch of the pinned buffer, allocator warm-up)
     ctx.download_into(host)
     barrier()
+    allocs0 = ctx.info().slot_allocs
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
         ctx.reset_counters()
@@ -400,6 +401,7 @@ def main():
     dt = allmax(time.perf_counter() - t0)
     e2e = {"value": allsum(moves_e2e) / dt, "unit": "moves/s", "h2d_bytes_per_step": h2d // args.e2e_steps,
            "d2h_bytes_per_step": d2h // args.e2e_steps, "steps": args.e2e_steps,
+           "ms_per_step": 1e3 * dt / args.e2e_steps, "slot_reallocations": ctx.info().slot_allocs - allocs0,
            "what": "mc2d_upload(host xy) + %d sweeps + energy/virial + mc2d_download(host xy) per step" % S}
 
     # ---- CPU baseline: the reference itself on this box's host cores (rank 0, N=1 only) -------------

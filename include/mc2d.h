@@ -248,6 +248,8 @@ typedef struct {
     int sweep_kernel_lanes; /* lanes per cell of the sweep kernel last launched: 4 or 8 (k_sweep_p), 32 (k_sweep) */
     double k_halo_ms;       /* with kernel timing on: summed halo push + sync time of the last mc2d_run_sweeps */
     long long k_halo_launches;
+    long long slot_allocs; /* how often the slot storage was (re-)allocated: an upload whose cells need more slots than
+                            * the storage has, or far fewer, re-allocates (and re-maps the neighbours' memory) */
 } mc2d_info;
 int mc2d_get_info(mc2d_ctx *ctx, mc2d_info *out);
 /* on != 0: bracket every sweep / re-bin kernel with CUDA events (adds launch gaps: use it for the

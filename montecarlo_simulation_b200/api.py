@@ -68,7 +68,8 @@ class Info(C.Structure):
                 ("last_pair_evals", C.c_longlong), ("k_sweep_ms", C.c_double), ("k_sweep_launches", C.c_longlong),
                 ("k_rebin_ms", C.c_double), ("k_rebin_launches", C.c_longlong),
                 ("halo_mode", C.c_int), ("sweep_kernel_lanes", C.c_int),
-                ("k_halo_ms", C.c_double), ("k_halo_launches", C.c_longlong)]
+                ("k_halo_ms", C.c_double), ("k_halo_launches", C.c_longlong),
+                ("slot_allocs", C.c_longlong)]
 
 
 # every symbol include/mc2d.h declares (tests check the library exports exactly these)

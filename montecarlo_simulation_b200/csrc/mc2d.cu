@@ -135,6 +135,7 @@ struct mc2d_ctx {
     int *cnt[2] = {nullptr, nullptr};
     int *ids[2] = {nullptr, nullptr};
     int allocK = 0;
+    long long slot_allocs = 0;
     // One arena holds the sync flags and both slot buffers: a neighbour rank maps it with ONE CUDA IPC
     // handle and writes its boundary column straight into this rank's ghost column over NVLink.
     char *arena = nullptr;
@@ -694,6 +695,7 @@ static int alloc_slots(mc2d_ctx *ctx, int K) {
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->allocK = K;
     ctx->g.K = K;
+    ctx->slot_allocs++;
     return MC2D_OK;
 }
 
@@ -713,6 +715,18 @@ static int auto_capacity(const mc2d_ctx *ctx, int maxcount) {
     int K = std::max(8, std::max(maxcount + maxcount / 2 + 4, (int)ceil(bound)));
     if (ctx->prm.cell_capacity > 0) K = std::max(ctx->prm.cell_capacity, maxcount);
     return even_up(K, 4);
+}
+
+// Capacity for an upload whose fullest cell holds maxcount particles.  Existing storage is kept while it still
+// leaves 25 % + 2 slots of headroom and is not more than twice what a fresh allocation would take: the largest
+// count of a big system moves by one or two between uploads, and a re-allocation costs a cudaMalloc plus, with
+// neighbours, closing and re-mapping their memory.  (The capacity does not enter the trajectory.)
+static int choose_capacity(const mc2d_ctx *ctx, int maxcount) {
+    const int want = auto_capacity(ctx, maxcount);
+    if (ctx->allocK > 0 && ctx->prm.cell_capacity <= 0 && ctx->allocK >= even_up(maxcount + maxcount / 4 + 2, 4) &&
+        ctx->allocK <= 2 * want)
+        return ctx->allocK;
+    return want;
 }
 
 static int energy_on_slots(mc2d_ctx *ctx, double *U, double *W, long long *N, bool resync, bool allreduce);
@@ -799,7 +813,7 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
         if (maxcount == kOutOfBox)
             FAIL(MC2D_ERR_OUT_OF_BOX, "a position is NaN or outside [0,%g] x [0,%g]", ctx->prm.Lx, ctx->prm.Ly);
         test_lag();
-        if (auto_capacity(ctx, maxcount) != ctx->allocK) {
+        if (choose_capacity(ctx, maxcount) != ctx->allocK) {
             direct = false;  // the cells got fuller (or much emptier) than the storage was made for: sorted path
         } else {
             k_order_cells<<<(nown * 8 + 255) / 256, 256, 0, ctx->stream>>>(
@@ -823,7 +837,7 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
             if ((rc = comm_max_int(ctx, &maxcount))) return rc;
         if (maxcount == kOutOfBox)
             FAIL(MC2D_ERR_OUT_OF_BOX, "a position is NaN or outside [0,%g] x [0,%g]", ctx->prm.Lx, ctx->prm.Ly);
-        int K = auto_capacity(ctx, maxcount);
+        int K = choose_capacity(ctx, maxcount);
         if (K > 1024)
             FAIL(MC2D_ERR_CELL_OVERFLOW, "a cell holds %d particles; capacity %d exceeds the 1024-slot limit", maxcount, K);
         if (K != ctx->allocK || (ctx->use_ids && !ctx->ids[0])) {
@@ -2051,6 +2065,7 @@ extern "C" int mc2d_get_info(mc2d_ctx *ctx, mc2d_info *o) {
     o->halo_mode = !ctx->g.ghost ? 0 : (ctx->p2p ? 2 : 1);
     o->k_halo_ms = ctx->k_halo_ms;
     o->k_halo_launches = ctx->k_halo_launches;
+    o->slot_allocs = ctx->slot_allocs;
     o->sweep_kernel_lanes = ctx->last_G ? ctx->last_G : 32;
     return MC2D_OK;
 }

@@ -309,12 +309,14 @@ def test_reupload_of_a_denser_configuration_falls_back_to_the_sort(mc, oracle):
     Lx = Ly = 40.0
     calc = oracle.calc(1.0, 0.0, ol.LJ, 2.5)
     dilute = lattice(16, 16, Lx, Ly, 0.2, 3)
-    dense = lattice(44, 44, Lx, Ly, 0.02, 4)
+    dense = lattice(60, 60, Lx, Ly, 0.02, 4)  # ~14 per cell: more than the 25 % headroom of the dilute storage
     with mc.Context(Lx, Ly, 2.5) as ctx:
         ctx.upload(dilute)
         k0 = ctx.info().cell_capacity
+        a0 = ctx.info().slot_allocs
         ctx.upload(dense)
-        assert ctx.info().cell_capacity >= k0 and ctx.num_particles() == len(dense)
+        assert ctx.info().slot_allocs == a0 + 1  # re-allocated by the sorted path
+        assert ctx.info().cell_capacity > k0 and ctx.num_particles() == len(dense)
         assert relerr(ctx.total_energy_virial()[0], oracle.total_energy_celllist(calc, Lx, Ly, dense)) < REL
         ctx.upload(dilute)
         assert ctx.num_particles() == len(dilute)
