@@ -145,3 +145,59 @@ def test_the_checker_catches_a_broken_protocol():
         except Violation:
             caught += 1
     assert caught > 100
+
+
+# ---- re-upload into live storage (mc2d_upload with nranks > 1) ---------------------------------------------------------
+# After the collective that agrees on the cell capacity every rank converts ITS cells and pushes its two boundary
+# columns; nothing orders one rank's conversion against a neighbour's push.  The conversion must therefore leave the
+# ghost columns alone (k_csr_to_slots / k_order_cells write owned cells only).  The broken variant is what the first
+# version did: the conversion also reset the ghost counts.
+
+def upload_program(rk, ranks, seq0, broken):
+    left, right = ranks[(rk.r - 1) % rk.n], ranks[(rk.r + 1) % rk.n]
+    yield  # ... arrives from the collective at its own time
+    rk.col = [1, 1]  # the new configuration of my boundary columns
+    if broken:
+        yield
+        rk.ghost[0] = [0, 0]  # conversion kernel writes the ghost counts too
+    yield
+    left.ghost[0][1] = rk.col[0]
+    yield
+    right.ghost[0][0] = rk.col[1]
+    left.flag[1] = max(left.flag[1], seq0 + 1)
+    right.flag[0] = max(right.flag[0], seq0 + 1)
+    while rk.flag[0] < seq0 + 1 or rk.flag[1] < seq0 + 1:
+        yield
+    if rk.ghost[0] != [1, 1]:
+        raise Violation("rank %d reads ghosts %r after the upload" % (rk.r, rk.ghost[0]))
+
+
+def simulate_upload(n, seed, broken=False):
+    rng = random.Random(seed)
+    ranks = [Rank(r, n) for r in range(n)]
+    gens = [upload_program(rk, ranks, 0, broken) for rk in ranks]
+    alive = list(range(n))
+    steps = 0
+    while alive:
+        i = rng.choice(alive) if rng.random() < 0.6 else alive[-1]  # the last rank is often far ahead
+        try:
+            next(gens[i])
+        except StopIteration:
+            alive.remove(i)
+        steps += 1
+        if steps > 100000:
+            raise Violation("deadlock")
+    return True
+
+
+@pytest.mark.parametrize("n", [2, 3, 8])
+def test_upload_leaves_ghost_columns_to_the_neighbour(n):
+    for seed in range(300):
+        assert simulate_upload(n, seed)
+    caught = 0
+    for seed in range(300):
+        try:
+            simulate_upload(n, seed, broken=True)
+        except Violation:
+            caught += 1
+    assert caught > 30
