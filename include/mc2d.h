@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MC2D_ABI_VERSION 1
+#define MC2D_ABI_VERSION 2
 
 typedef enum {
     MC2D_OK = 0,
@@ -35,7 +35,10 @@ typedef enum {
     MC2D_ERR_GEOMETRY = 5,      /* box too small for the checkerboard (needs >= 2 cells of side >= rcut per direction, even counts per slab) */
     MC2D_ERR_OUT_OF_BOX = 6,    /* a position is NaN or outside [0,Lx] x [0,Ly] */
     MC2D_ERR_NCCL = 7,
-    MC2D_ERR_STATE = 8          /* call out of order (e.g. sweep before upload) */
+    MC2D_ERR_STATE = 8,         /* call out of order (e.g. sweep before upload) */
+    MC2D_ERR_PEER_TIMEOUT = 9   /* a neighbour rank did not signal its halo within tuning.spin_timeout_ms (it failed,
+                                 * returned early or died): the kernel gave up waiting instead of hanging.  The slab
+                                 * contexts of ALL ranks are out of step afterwards and must be destroyed. */
 } mc2d_status;
 
 /* PotentialType, in the order of serial_src/potential.h:11-18 */
@@ -226,6 +229,33 @@ int mc2d_rescale_finish(mc2d_ctx *ctx, int accept);
 int mc2d_probe_point(mc2d_ctx *ctx, double x, double y, double *dU);
 int mc2d_probe_particle(mc2d_ctx *ctx, long long index, double *x, double *y, double *dU);
 int mc2d_apply_probe(mc2d_ctx *ctx, int what);
+
+/* -- tuning / A-B switches -------------------------------------------------------------------------
+ * Every variant gives the same trajectory (tests/test_gpu_parity.py::test_sweep_kernel_variants_are_bit_identical).
+ * mc2d_create fills the defaults; mc2d_get_tuning / mc2d_set_tuning read and replace them between calls.  The
+ * library reads no environment variables. */
+typedef struct {
+    int sweep_lanes;          /* -1 auto (4, or 8 for very full cells); 0: k_sweep, one warp per cell; 2, 4, 8: lanes per
+                               * cell of k_sweep_p */
+    int sweep_slots;          /* 0 auto; candidate slots of shared memory per warp of k_sweep_p (raised to one full cell
+                               * neighbourhood) */
+    int sweep_warps_per_cta;  /* 0 auto (8) */
+    int fuse_passes;          /* 1: the four colour passes of a sweep are ONE cooperative launch; 0: one launch per pass */
+    int pipeline;             /* 1: per-column-pair completion counters between the colours; 0: grid barrier */
+    int fuse_rebin;           /* 1: re-bin after the grid shift + work order are phase 0 of the sweep launch (single rank);
+                               * 0: separate k_rebin4 / k_order_local launches */
+    int rebin_lanes;          /* 4 (default) or 8 lanes per new cell in the re-bin */
+    int energy_unstaged;      /* 1: k_energy_virial_g instead of k_energy_p */
+    int halo_nccl;            /* 1: ncclSend/ncclRecv of whole columns instead of stores into the neighbours' memory */
+    int halo_overlap;         /* 1: slab-edge work overlaps the interior (second stream / inside the sweep kernel) */
+    int upload_sort;          /* 1: every mc2d_upload takes the key-sort path (default: direct binning on re-upload) */
+    int spin_timeout_ms;      /* budget of every in-kernel wait on a neighbour's flag word; 0 = default (10 000 ms) */
+    int test_upload_lag_us;   /* fault injection for tools/check_multi_gpu.py (odd ranks sleep after the capacity collective
+                               * of an upload); honoured only by a library built with -DMC2D_FAULT_INJECTION */
+    int reserved[3];
+} mc2d_tuning;
+int mc2d_get_tuning(mc2d_ctx *ctx, mc2d_tuning *out);
+int mc2d_set_tuning(mc2d_ctx *ctx, const mc2d_tuning *in);
 
 /* -- introspection for benchmarks ------------------------------------------------------------ */
 typedef struct {

@@ -17,7 +17,8 @@ LIB_PATH = os.environ.get("MC2D_LIB", os.path.join(PKG, "libmc2d.so"))  # MC2D_L
 LENNARD_JONES, WCA, YUKAWA, ATHERMAL_STAR, THERMAL_STAR, IDEAL = range(6)
 POTENTIAL_NAMES = {"LennardJones": 0, "WCA": 1, "Yukawa": 2, "AthermalStar": 3, "ThermalStar": 4, "Ideal": 5}
 
-OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_CELL_OVERFLOW, ERR_GEOMETRY, ERR_OUT_OF_BOX, ERR_NCCL, ERR_STATE = range(9)
+(OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_CELL_OVERFLOW, ERR_GEOMETRY, ERR_OUT_OF_BOX, ERR_NCCL, ERR_STATE,
+ ERR_PEER_TIMEOUT) = range(10)
 UNIQUE_ID_BYTES = 128
 
 
@@ -72,6 +73,15 @@ class Info(C.Structure):
                 ("slot_allocs", C.c_longlong)]
 
 
+class Tuning(C.Structure):
+    """mc2d_tuning: A-B switches (every variant gives the same trajectory); the library reads no environment"""
+    _fields_ = [("sweep_lanes", C.c_int), ("sweep_slots", C.c_int), ("sweep_warps_per_cta", C.c_int),
+                ("fuse_passes", C.c_int), ("pipeline", C.c_int), ("fuse_rebin", C.c_int), ("rebin_lanes", C.c_int),
+                ("energy_unstaged", C.c_int), ("halo_nccl", C.c_int), ("halo_overlap", C.c_int),
+                ("upload_sort", C.c_int), ("spin_timeout_ms", C.c_int), ("test_upload_lag_us", C.c_int),
+                ("reserved", C.c_int * 3)]
+
+
 # every symbol include/mc2d.h declares (tests check the library exports exactly these)
 EXPORTS = [
     "mc2d_status_string", "mc2d_last_error", "mc2d_abi_version", "mc2d_device_count", "mc2d_create", "mc2d_destroy",
@@ -82,6 +92,7 @@ EXPORTS = [
     "mc2d_comm_unique_id", "mc2d_comm_init", "mc2d_allreduce_stats", "mc2d_get_info", "mc2d_get_stream",
     "mc2d_synchronize", "mc2d_set_kernel_timing", "mc2d_calc_neighbor_list", "mc2d_calc_energy_virial_bruteforce",
     "mc2d_rescale_try", "mc2d_rescale_finish", "mc2d_probe_point", "mc2d_probe_particle", "mc2d_apply_probe", "mc2d_measure_fp64_peak",
+    "mc2d_get_tuning", "mc2d_set_tuning",
 ]
 
 _lib = None
@@ -138,6 +149,8 @@ def load_library() -> C.CDLL:
     L.mc2d_probe_particle.argtypes = [vp, ll, dp, dp, dp]
     L.mc2d_apply_probe.argtypes = [vp, i]
     L.mc2d_measure_fp64_peak.argtypes = [vp, dp]
+    L.mc2d_get_tuning.argtypes = [vp, C.POINTER(Tuning)]
+    L.mc2d_set_tuning.argtypes = [vp, C.POINTER(Tuning)]
     _lib = L
     return L
 
@@ -217,7 +230,7 @@ class Context:
 
     def __init__(self, Lx, Ly, rcut, potential=LENNARD_JONES, T=1.0, activity=0.0, delta=0.1, seed=1, f=0.0,
                  alpha=0.0, A0=0.0, kappa=0.0, device=0, rank=0, nranks=1, cell_capacity=0, p_insert=0.0,
-                 p_delete=0.0, cell_margin=0.0):
+                 p_delete=0.0, cell_margin=0.0, tuning=None):
         self.L = load_library()
         if isinstance(potential, str):
             potential = POTENTIAL_NAMES[potential]
@@ -232,6 +245,23 @@ class Context:
                 self.L.mc2d_destroy(self.h)
                 self.h = C.c_void_p()
             raise MC2DError(rc, detail)
+        if tuning:
+            self.set_tuning(**tuning)
+
+    # -- tuning (mc2d_tuning) -------------------------------------------------------------------
+    def tuning(self) -> dict:
+        t = Tuning()
+        self._check(self.L.mc2d_get_tuning(self.h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in Tuning._fields_ if n != "reserved"}
+
+    def set_tuning(self, **kw):
+        t = Tuning()
+        self._check(self.L.mc2d_get_tuning(self.h, C.byref(t)))
+        for k, v in kw.items():
+            if k == "reserved" or not hasattr(t, k):
+                raise KeyError("unknown tuning field %r" % k)
+            setattr(t, k, int(v))
+        self._check(self.L.mc2d_set_tuning(self.h, C.byref(t)))
 
     # -- helpers -------------------------------------------------------------------------------
     def _check(self, rc):

@@ -268,6 +268,8 @@ struct HaloArgs {
     int wait[2];                   // wait for the left / right neighbour's signal
     int ny, K;
     unsigned long long seq;
+    int *err;                           // ctx->d_err: [4] is set when a wait gives up
+    unsigned long long spin_budget_ns;  // budget of the wait (mc2d_tuning.spin_timeout_ms)
 };
 
 __global__ void __launch_bounds__(256) k_halo_sync(HaloArgs h) {
@@ -296,8 +298,8 @@ __global__ void __launch_bounds__(256) k_halo_sync(HaloArgs h) {
                 *(volatile unsigned long long *)h.dflag[1] = h.seq;
                 __threadfence_system();
             }
-            const volatile unsigned long long *f = h.myflag;
-            while ((h.wait[0] && f[0] < h.seq) || (h.wait[1] && f[1] < h.seq)) __nanosleep(32);
+            if (h.wait[0]) spin_until_ge(h.myflag + 0, h.seq, h.err, h.spin_budget_ns);
+            if (h.wait[1]) spin_until_ge(h.myflag + 1, h.seq, h.err, h.spin_budget_ns);
             __threadfence_system();
         }
     }

@@ -101,7 +101,7 @@ inline int even_up(int v, int m) { return ((v + m - 1) / m) * m; }
 // One named field per use, so nested helpers (count_particles inside fetch_stats ...) never alias.
 struct PinnedScalars {
     int flags[4];
-    int errv[4];
+    int errv[8];
     int maxcount, ovf, csr_kept, pad;
     unsigned long long kept, count, tn;
     unsigned long long ps[2];
@@ -145,7 +145,7 @@ struct mc2d_ctx {
     bool p2p = false;                         // halo over peer memory (k_halo_sync); false: ncclSend/ncclRecv
     unsigned long long halo_seq = 0;          // sync points so far; every rank counts the same ones
     int last_G = 0;                           // lanes per cell of the last sweep launch (0: k_sweep)
-    int fuse_passes = 1;                      // MC2D_SWEEP_FUSE=0: one launch per colour pass (A-B tests)
+    mc2d_tuning tune{};                       // A-B switches (mc2d_set_tuning); the library reads no environment
     bool auto_margin = false;                 // cell_margin = -1: the cell width is chosen at the first upload
     // NPT volume move in flight (mc2d_rescale_try): the rescaled configuration sits in the spare buffer
     double *d_probe = nullptr;  // [0] dU, [1] x, [2] y of the last single-particle probe
@@ -158,11 +158,11 @@ struct mc2d_ctx {
     unsigned long long *d_counters = nullptr;  // 8
     double *d_energy = nullptr;                // [0] running, [1] U, [2] W, [3] N
     unsigned long long *d_pair_stats = nullptr;  // 2 + [2] particle count
-    int *d_err = nullptr;                      // [0] overflow need, [1] flags, [2] max count
+    int *d_err = nullptr;                      // [0] overflow need, [1] flags, [2] max count, [3] energy item did not fit,
+                                               // [4] an in-kernel wait gave up (never cleared), [5] insertions refused in this call
     DevBuf partial, trace_buf;
     DevBuf order_buf;  // work order of k_sweep_p (k_order_local), rebuilt after every re-bin
     DevBuf done_buf;   // k_sweep_p pipeline: finished items per (colour pass, column pair)
-    int pipeline = 1;  // MC2D_SWEEP_PIPELINE=0: grid barrier between the colours of a fused sweep (A-B tests)
     bool order_valid = false;
     int *d_work = nullptr;  // work-item ticket counters: [p] interior / whole pass p of a sweep, [4 + p] slab boundary
     int num_sms = 0;
@@ -178,6 +178,7 @@ struct mc2d_ctx {
     PinnedScalars *hp = nullptr;  // cudaHostAlloc
     std::map<const void *, LaunchShape> launch_shapes;  // per kernel: shape whose attribute / occupancy is cached
     long long n_last = 0;             // last known particle count (sizes the neighbour staging area)
+    int last_refused = 0;             // insertions refused (cell full) by the last mc2d_run_sweeps call
     bool ktiming = false;
     std::vector<cudaEvent_t> kev;  // event pool for per-kernel timing
     std::vector<int> kev_kind;     // 0 sweep, 1 rebin (one entry per event PAIR used in this call)
@@ -233,6 +234,7 @@ extern "C" const char *mc2d_status_string(int s) {
     case MC2D_ERR_OUT_OF_BOX: return "position outside the box or NaN";
     case MC2D_ERR_NCCL: return "NCCL error";
     case MC2D_ERR_STATE: return "call out of order";
+    case MC2D_ERR_PEER_TIMEOUT: return "a neighbour rank did not signal its halo in time";
     }
     return "unknown status";
 }
@@ -331,6 +333,37 @@ static int setup_grid(mc2d_ctx *ctx, double margin) {
     return MC2D_OK;
 }
 
+static mc2d_tuning default_tuning() {
+    mc2d_tuning t;
+    memset(&t, 0, sizeof t);
+    t.sweep_lanes = -1;
+    t.fuse_passes = 1;
+    t.pipeline = 1;
+    t.fuse_rebin = 1;
+    t.rebin_lanes = 4;
+    t.halo_overlap = 1;
+    return t;
+}
+
+extern "C" int mc2d_get_tuning(mc2d_ctx *ctx, mc2d_tuning *out) {
+    if (!ctx || !out) return MC2D_ERR_INVALID;
+    *out = ctx->tune;
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_set_tuning(mc2d_ctx *ctx, const mc2d_tuning *in) {
+    if (!ctx || !in) return MC2D_ERR_INVALID;
+    const int G = in->sweep_lanes;
+    if (G != -1 && G != 0 && G != 2 && G != 4 && G != 8) FAIL(MC2D_ERR_INVALID, "tuning.sweep_lanes must be -1, 0, 2, 4 or 8");
+    if (in->rebin_lanes != 4 && in->rebin_lanes != 8) FAIL(MC2D_ERR_INVALID, "tuning.rebin_lanes must be 4 or 8");
+    if (in->sweep_slots < 0 || in->sweep_warps_per_cta < 0 || in->sweep_warps_per_cta > 8 || in->spin_timeout_ms < 0 ||
+        in->test_upload_lag_us < 0)
+        FAIL(MC2D_ERR_INVALID, "tuning: negative or out-of-range value");
+    if (in->halo_nccl != ctx->tune.halo_nccl) ctx->peers_valid = false;  // the next exchange re-negotiates the halo mode
+    ctx->tune = *in;
+    return MC2D_OK;
+}
+
 extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
     if (!p || !out) return MC2D_ERR_INVALID;
     *out = nullptr;
@@ -357,6 +390,7 @@ extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
     if (p->cell_margin != -1.0 && (!(p->cell_margin >= 0) || p->cell_margin > 3))
         FAIL(MC2D_ERR_INVALID, "mc2d_create: cell_margin must be in [0, 3], or -1 (chosen from the density at the first upload)");
     ctx->auto_margin = (p->cell_margin == -1.0);
+    ctx->tune = default_tuning();
     if (int rc = setup_grid(ctx, ctx->auto_margin ? 0.0 : p->cell_margin)) return rc;
     CU(cudaSetDevice(ctx->dev));
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -368,7 +402,7 @@ extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
     CU(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
     CU(cudaMalloc(&ctx->d_energy, 4 * sizeof(double)));
     CU(cudaMalloc(&ctx->d_pair_stats, 4 * sizeof(unsigned long long)));
-    CU(cudaMalloc(&ctx->d_err, 4 * sizeof(int)));
+    CU(cudaMalloc(&ctx->d_err, 8 * sizeof(int)));
     CU(cudaMalloc(&ctx->d_work, 8 * sizeof(int)));
     CU(cudaMalloc(&ctx->d_probe, 4 * sizeof(double)));
     CU(cudaMalloc(&ctx->d_probe_sel, 2 * sizeof(int)));
@@ -378,9 +412,24 @@ extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
     memset(ctx->hp, 0, sizeof(PinnedScalars));
     CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_energy, 0, 4 * sizeof(double), ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_err, 0, 8 * sizeof(int), ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return MC2D_OK;
+}
+
+static unsigned long long spin_budget_ns(const mc2d_ctx *ctx) {
+    const int ms = ctx->tune.spin_timeout_ms > 0 ? ctx->tune.spin_timeout_ms : 10000;
+    return (unsigned long long)ms * 1000000ull;
+}
+
+// after a synchronisation that followed halo kernels: did one of their waits give up?  (errv = copy of d_err)
+static int check_peer_timeout(mc2d_ctx *ctx, const int *errv) {
+    if (!errv[4]) return MC2D_OK;
+    ctx->have_particles = false;
+    FAIL(MC2D_ERR_PEER_TIMEOUT,
+         "a neighbour rank did not signal its halo within %d ms (it failed, returned early or died); the slab contexts "
+         "of all ranks are out of step: destroy them",
+         ctx->tune.spin_timeout_ms > 0 ? ctx->tune.spin_timeout_ms : 10000);
 }
 
 static void close_peers(mc2d_ctx *ctx) {
@@ -540,9 +589,7 @@ static int connect_peers(mc2d_ctx *ctx) {
 #if MC2D_HAVE_NCCL_H
     const int R = ctx->prm.nranks, me = ctx->prm.rank;
     close_peers(ctx);
-    int ok = 1;
-    if (const char *e = getenv("MC2D_HALO"))
-        if (!strcmp(e, "nccl")) ok = 0;
+    int ok = ctx->tune.halo_nccl ? 0 : 1;
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof mine);
     if (ok && cudaIpcGetMemHandle(&mine, ctx->arena) != cudaSuccess) {
@@ -616,6 +663,8 @@ static int halo_exchange(mc2d_ctx *ctx, int buf, bool left, bool right, bool wai
         h.K = g.K;
         if (signal) ++ctx->halo_seq;  // a launch that only waits waits for the sync point reached last
         h.seq = ctx->halo_seq;
+        h.err = ctx->d_err;
+        h.spin_budget_ns = spin_budget_ns(ctx);
         const int total = (int)colp * (h.push[0] + h.push[1]);
         const int nblk = std::max(1, std::min(4 * ctx->num_sms, (total + 255) / 256));
         k_halo_sync<<<nblk, 256, 0, stream ? stream : ctx->stream>>>(h);
@@ -773,14 +822,15 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
     // A bad position on one rank fails the upload on every rank: the flag travels with the collective maximum.
     constexpr int kOutOfBox = 0x7fffffff;
     auto test_lag = [&]() {
-        if (const char *e = getenv("MC2D_TEST_UPLOAD_LAG_US"))
-            if ((ctx->prm.rank & 1) && atoi(e) > 0) usleep((useconds_t)atoi(e));
+#ifdef MC2D_FAULT_INJECTION
+        if ((ctx->prm.rank & 1) && ctx->tune.test_upload_lag_us > 0) usleep((useconds_t)ctx->tune.test_upload_lag_us);
+#endif
     };
     // Slot storage of a fitting capacity already exists (a re-upload): bin straight into the spare buffer, no sort.
     // Every rank takes the same branch: allocK and use_ids are the same on all ranks, and so is the capacity
     // computed from the global maximum below.
     bool direct = ctx->arena && ctx->allocK > 0 && g.K == ctx->allocK && (!ctx->use_ids || ctx->ids[0]) &&
-                  !getenv("MC2D_UPLOAD_SORT");
+                  !ctx->tune.upload_sort;
     const bool was_direct = direct;
     if (direct) {
         ctx->have_particles = false;  // the spare buffer may be the current one: a failed upload leaves nothing
@@ -871,8 +921,11 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
         rc = energy_on_slots(ctx, &U, &W, &N, true, false);
         if (rc) return rc;
     }
+    if (g.ghost) CU(cudaMemcpyAsync(ctx->hp->errv, ctx->d_err, sizeof ctx->hp->errv, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
+    if (g.ghost)
+        if ((rc = check_peer_timeout(ctx, ctx->hp->errv))) return rc;
     return MC2D_OK;
 }
 
@@ -1011,6 +1064,7 @@ static int launch_energy_items(mc2d_ctx *ctx, double *U, double *W, bool *done) 
     *done = false;
     const Grid &g = ctx->g;
     if (g.nx < 4 || g.ny < 4) return MC2D_OK;
+    if (sizeof(int) * (size_t)(3 * g.ny + g.ny / 2) > 200 * 1024) return MC2D_OK;  // too tall for k_order_local
     ItemLayout lay;
     if (int rc = item_layout(ctx, &lay)) return rc;
     if (!lay.G) return MC2D_OK;
@@ -1114,7 +1168,7 @@ static int energy_on_slots(mc2d_ctx *ctx, double *U, double *W, long long *N, bo
     int rc = MC2D_OK;
     // the particle count rides on the synchronisation of the energy launch
     if ((rc = count_particles_async(ctx))) return rc;
-    if (!getenv("MC2D_ENERGY_UNSTAGED")) rc = launch_energy_items(ctx, U, W, &done);
+    if (!ctx->tune.energy_unstaged) rc = launch_energy_items(ctx, U, W, &done);
     if (rc) return rc;
     if (!done) rc = launch_energy(ctx, v, g.ncol * g.ny, half, false, nullptr, nullptr, U, W);
     if (rc) return rc;
@@ -1548,21 +1602,21 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     // one cell with all its neighbours cannot fit a warp's slots; then k_sweep (one warp per cell).
     // MC2D_SWEEP_G overrides the lanes per cell (0 = k_sweep), for tuning and tests.
     int G = 0, R = 0;
-    if (!minimg && K <= 255) {
+    const bool order_fits = sizeof(int) * (size_t)(3 * g.ny + g.ny / 2) <= 200 * 1024;  // k_order_local's shared memory
+    if (!minimg && K <= 255 && order_fits) {
         const double n_c = (double)std::max<long long>(ctx->n_last, 1) / std::max(1, g.ncol * g.ny);
         G = (9.0 * n_c > 64.0) ? 8 : 4;
-        if (const char *e = getenv("MC2D_SWEEP_G")) G = atoi(e);
-        if (G != 0 && G != 2 && G != 4 && G != 8) FAIL(MC2D_ERR_INVALID, "MC2D_SWEEP_G must be 0, 2, 4 or 8");
+        if (ctx->tune.sweep_lanes >= 0) G = ctx->tune.sweep_lanes;
         if (G) {
             const size_t slot_bytes = sizeof(double2) + (ctx->use_ids ? sizeof(int) : 0);
             const int need_max = (ideal ? 0 : 8 * K) + K;  // one cell, every slot of its neighbourhood full
             wpb = 8;
-            if (const char *e = getenv("MC2D_SWEEP_WPB")) wpb = std::max(1, std::min(8, atoi(e)));  // tuning
+            if (ctx->tune.sweep_warps_per_cta > 0) wpb = ctx->tune.sweep_warps_per_cta;
             // 6 KB per warp: 3 CTAs x 8 warps per SM (the register limit) with ~80 KB of the SM left as L1 for the
             // count / order / position loads.  Measured on config #4: 61 us per pass for R = 320..512 slots,
             // 67 us at 576 (the third CTA no longer fits), 79 us at 256 (one item in four runs in two batches).
             R = (int)((6 * 1024) / slot_bytes) & ~3;  // a multiple of 4: the warps' regions stay 16-byte aligned with ids
-            if (const char *e = getenv("MC2D_SWEEP_R")) R = (std::max(need_max, atoi(e)) + 3) & ~3;  // tuning
+            if (ctx->tune.sweep_slots > 0) R = (std::max(need_max, ctx->tune.sweep_slots) + 3) & ~3;
             if (R < need_max) {  // big cells: fewer warps per SM
                 R = (need_max + 3) & ~3;
                 while (wpb > 1 && (size_t)R * slot_bytes * wpb > 200 * 1024) wpb >>= 1;
@@ -1588,12 +1642,10 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
         CU(cudaMemsetAsync(ctx->d_trace_n, 0, sizeof(unsigned long long), ctx->stream));
     }
     const int ncell_owned = g.ncol * g.ny;
-    int rebin_G = 4;
-    if (const char *e = getenv("MC2D_REBIN_G")) rebin_G = atoi(e);
+    const int rebin_G = ctx->tune.rebin_lanes;
     ctx->kev_kind.clear();
-    if (const char *e = getenv("MC2D_SWEEP_FUSE")) ctx->fuse_passes = atoi(e);
-    if (const char *e = getenv("MC2D_SWEEP_PIPELINE")) ctx->pipeline = atoi(e);
     CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_err + 5, 0, sizeof(int), ctx->stream));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     // Slab mode with peer-memory halos: the boundary column pair of a pass (and the two boundary columns of
     // a re-bin) run on a second stream, followed there by the push into the neighbour and the signal, while
@@ -1604,7 +1656,7 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     if (overlap && !ctx->peers_valid)
         if (int rc = connect_peers(ctx)) return rc;
     overlap = overlap && ctx->p2p;
-    if (const char *e = getenv("MC2D_HALO_OVERLAP")) overlap = overlap && atoi(e) != 0;
+    overlap = overlap && ctx->tune.halo_overlap != 0;
     cudaStream_t sa = ctx->stream, sb = ctx->stream_b;
     auto join = [&]() -> int {  // each stream continues after everything queued so far on the other one
         CU(cudaEventRecord(ctx->ev_a, sa));
@@ -1685,10 +1737,10 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
         }
         // single rank / no overlap: the four passes of a sweep go out as ONE cooperative launch (grid barrier between
         // colours); MC2D_SWEEP_FUSE=0 launches them one by one
-        const bool fuse = persistent && !overlap && !g.ghost && ctx->fuse_passes;
+        const bool fuse = persistent && !overlap && !g.ghost && ctx->tune.fuse_passes;
         // slab mode: the same single launch, with the halo exchange inside the kernel (boundary items wait on the
         // neighbour's flag word, push their cells into its ghost column, the last one signals)
-        const bool fuse_halo = overlap && ctx->fuse_passes && (nitems / npairs) <= ctx->num_sms * wpb;
+        const bool fuse_halo = overlap && ctx->tune.fuse_passes && (nitems / npairs) <= ctx->num_sms * wpb;
         for (int p = 0; p < ((fuse || fuse_halo) ? 1 : 4); ++p) {
             SweepArgs a;
             a.pos = ctx->pos[ctx->cur];
@@ -1702,7 +1754,7 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             a.npass = (fuse || fuse_halo) ? 4 : 1;
             for (int q = 0; q < 4; ++q) a.colours[q] = order[q];
             a.dU_stride = nblocks;
-            a.pipeline = (fuse && ctx->pipeline) ? 1 : 0;
+            a.pipeline = (fuse && ctx->tune.pipeline) ? 1 : 0;
             a.done = ctx->done_buf.as<int>();
             a.halo_fused = 0;
             a.myflag = nullptr;
@@ -1732,6 +1784,8 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             a.p_del = ctx->p_del;
             a.partial_dU = ctx->partial.as<double>() + (size_t)p * nblocks;
             a.counters = ctx->d_counters;
+            a.err = ctx->d_err;
+            a.spin_budget_ns = spin_budget_ns(ctx);
             a.trace = trace ? ctx->trace_buf.as<mc2d_trial>() : nullptr;
             a.trace_n = ctx->d_trace_n;
             a.trace_cap = trace_cap;
@@ -1868,11 +1922,15 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
         if (ncopy > 0) CU(cudaMemcpy(trace, ctx->trace_buf.p, sizeof(mc2d_trial) * (size_t)ncopy, cudaMemcpyDeviceToHost));
         if (trace_n) *trace_n = (long long)tn;
     }
-    if (errv[0] > K)
+    if (int rc = check_peer_timeout(ctx, errv)) return rc;
+    if (errv[0] > K) {
+        ctx->have_particles = false;
         FAIL(MC2D_ERR_CELL_OVERFLOW,
              "re-binning needed %d slots in one cell but cell_capacity is %d: particles were dropped, the "
              "configuration on the device is no longer valid; re-upload with a larger cell_capacity",
              errv[0], K);
+    }
+    ctx->last_refused = errv[5];
     return MC2D_OK;
 }
 
@@ -1902,10 +1960,13 @@ extern "C" int mc2d_run_sweeps(mc2d_ctx *ctx, long long nsweeps, const mc2d_swee
     if (st) {
         rc = fetch_stats(ctx, st);
         if (rc) return rc;
-        if (st->overflow > 0)
-            FAIL(MC2D_ERR_CELL_OVERFLOW, "%lld insertion(s) were refused because a cell had no free slot (capacity %d)",
-                 st->overflow, ctx->g.K);
     }
+    // A refused insertion biases the ensemble (detailed balance): it is reported whether or not the caller asked for
+    // the statistics, and per CALL (stats.overflow is the running total since mc2d_reset_counters).  The sweeps of this
+    // call have run and the statistics are valid; the caller re-uploads with a larger cell_capacity.
+    if (ctx->last_refused > 0)
+        FAIL(MC2D_ERR_CELL_OVERFLOW, "%d insertion(s) of this call were refused because a cell had no free slot (capacity %d)",
+             ctx->last_refused, ctx->g.K);
     return MC2D_OK;
 }
 

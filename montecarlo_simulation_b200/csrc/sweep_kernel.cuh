@@ -50,6 +50,8 @@ struct SweepArgs {
     double p_ins, p_del;
     double *partial_dU;            // one accumulator per CTA, private to it, summed at the end of the batch
     unsigned long long *counters;  // [0..2] attempted, [3..5] accepted, [6] overflow
+    int *err;                      // ctx->d_err: [4] a wait on a flag word gave up, [5] insertions refused in THIS call
+    unsigned long long spin_budget_ns;  // budget of one wait on a flag word (mc2d_tuning.spin_timeout_ms)
     mc2d_trial *trace;
     unsigned long long *trace_n;
     long long trace_cap;
@@ -394,5 +396,6 @@ __global__ void __launch_bounds__(256, MC2D_SWEEP_MIN_BLOCKS) k_sweep(SweepArgs 
         unsigned long long s = 0;
         for (int i = 0; i < wpb; ++i) s += cred[i][threadIdx.x];
         if (s) atomicAdd(&a.counters[threadIdx.x], s);
+        if (s && threadIdx.x == 6) atomicAdd(&a.err[5], (int)s);
     }
 }

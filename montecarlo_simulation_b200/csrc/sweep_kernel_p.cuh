@@ -166,6 +166,40 @@ __device__ __forceinline__ int warp_max_int(int v) {
 #define MC2D_SWEEPP_MIN_BLOCKS 3
 #endif
 
+// ------------------------------------------------------------------------------------------------
+// Bounded waits.  Every in-kernel wait on a word that another rank (or another warp) writes has a time
+// budget (mc2d_tuning.spin_timeout_ms): a neighbour that failed before its launch, returned early or
+// died must not hang this GPU inside a cooperative kernel.  When the budget runs out the waiter sets
+// err[4]; every other wait sees that word and gives up at once, the kernel drains (on garbage), and
+// the host returns MC2D_ERR_PEER_TIMEOUT and drops the configuration.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mc2d_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// one look inside a spin loop: true when the wait must be abandoned (t0 = 0 on the first call)
+__device__ __forceinline__ bool spin_expired(int *err, unsigned long long budget_ns, unsigned long long &t0) {
+    if (*(volatile int *)&err[4]) return true;
+    const unsigned long long now = mc2d_globaltimer();
+    if (t0 == 0) t0 = now;
+    if (now - t0 > budget_ns) {
+        atomicExch(&err[4], 1);
+        return true;
+    }
+    return false;
+}
+__device__ __forceinline__ bool spin_until_ge(const unsigned long long *flag, unsigned long long want, int *err,
+                                              unsigned long long budget_ns) {
+    const volatile unsigned long long *f = flag;
+    unsigned long long t0 = 0;
+    while (*f < want) {
+        if (spin_expired(err, budget_ns, t0)) return false;
+        __nanosleep(32);
+    }
+    return true;
+}
+
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -380,6 +414,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         if (!a.pipeline || psv == 0) return true;
         const int *d = a.done + (psv - 1) * npairs;
         const int pm = p == 0 ? npairs - 1 : p - 1, pp = p == npairs - 1 ? 0 : p + 1;
+        unsigned long long t0 = 0;
         for (;;) {
             int v0, v1, v2;
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v0) : "l"(d + pm) : "memory");
@@ -387,6 +422,9 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v2) : "l"(d + pp) : "memory");
             if (min(v0, min(v1, v2)) >= ipp) return true;
             if (!block) return false;
+            // bounded: these counters are written by this kernel only, so the budget can only run out on a bug or
+            // after another wait has already given up; the host then reports the failure instead of hanging
+            if (spin_expired(a.err, a.spin_budget_ns, t0)) return true;
             __nanosleep(64);
         }
     };
@@ -414,10 +452,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
     prof_bar += clock64() - pb0;
 #endif
     if (a.halo_fused && it0 < ipp) {  // boundary item: wait until the neighbour has completed the ghost column it reads
-        if (lane == 0) {
-            const volatile unsigned long long *f = a.myflag;
-            while (f[hside] < a.seq_base + (unsigned long long)ps) __nanosleep(32);
-        }
+        if (lane == 0) spin_until_ge(a.myflag + hside, a.seq_base + (unsigned long long)ps, a.err, a.spin_budget_ns);
         __syncwarp();
         __threadfence();
     }
@@ -748,5 +783,6 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         unsigned long long s = 0;
         for (int i = 0; i < wpb; ++i) s += cred[i][threadIdx.x];
         if (s) atomicAdd(&a.counters[threadIdx.x], s);
+        if (s && threadIdx.x == 6) atomicAdd(&a.err[5], (int)s);
     }
 }

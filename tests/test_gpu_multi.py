@@ -1,0 +1,89 @@
+"""Multi-rank GPU parity (-m gpu; needs at least two devices on the box, skipped otherwise): tools/check_multi_gpu.py
+under torchrun with 2 ranks (and 4 when the box has them).  What it pins is the reference contract of
+mpi_src/MC_parallel.cpp:57-114 (4-colour sweep with ghost refresh after every colour),
+particle_exchange.cpp:247-258,305-337 (ghost updates, ownership migration) and
+thermodynamic_calculator_parallel.cpp:56-134 (U, W all-reduced, cross-rank pairs counted once) — as the reference's
+own tests do (unit_test_mpi/test_mc_parallel.cpp:136-187,222-278; test_thermodynamic_calculator_parallel.cpp:378-514:
+N conserved, particles stay in the box and on their owner, energies equal the serial calculator's) — but tightened to
+BIT equality with the one-rank trajectory, which the counter-based Philox streams make possible."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _ndev():
+    from montecarlo_simulation_b200 import api
+
+    return api.device_count()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_slabs_reproduce_the_one_gpu_trajectory_bit_for_bit(world):
+    n = _ndev()
+    if n < world:
+        pytest.skip("needs %d CUDA devices, this box has %d" % (world, n))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", str(29600 + world), os.path.join(ROOT, "tools", "check_multi_gpu.py")]
+    res = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    sys.stdout.write(res.stdout[-4000:])
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "MISMATCH" not in res.stdout and res.stdout.count("-> OK") >= 6
+
+
+def test_peer_timeout_returns_a_status_instead_of_hanging():
+    """A rank whose neighbour never shows up must get MC2D_ERR_PEER_TIMEOUT back (bounded in-kernel waits), not hang
+    inside the cooperative sweep kernel: rank 1 uploads and then simply stops calling; rank 0 runs sweeps with a 300 ms
+    wait budget."""
+    if _ndev() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    code = r"""
+import os, sys, time
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+import montecarlo_simulation_b200 as m
+from montecarlo_simulation_b200 import api
+rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+L = 321.0
+g = np.stack(np.meshgrid(np.arange(227), np.arange(227), indexing="ij"), -1).reshape(-1, 2).astype(float)
+xy = (g + 0.5) * (L / 227)
+ctx = m.Context(L, L, 2.5, T=1.0, delta=0.1, seed=11, device=local, rank=rank, nranks=2, tuning=dict(spin_timeout_ms=300))
+ids = [api.comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(ids, src=0)
+ctx.comm_init(ids[0])
+ctx.upload(xy)
+ctx.run_sweeps(2)
+status = 0
+if rank == 0:
+    t0 = time.time()
+    try:
+        ctx.run_sweeps(3)          # the neighbour never launches its side
+    except m.MC2DError as e:
+        status = e.status
+    print("rank 0: status %%d after %%.2f s" %% (status, time.time() - t0), flush=True)
+    assert status == api.ERR_PEER_TIMEOUT, status
+else:
+    time.sleep(3.0)
+dist.barrier()
+os._exit(0)
+""" % ROOT
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29611", "-c", code]
+    # torchrun has no -c: write the script next to the test outputs
+    path = os.path.join(ROOT, "gpurun_out", "_timeout_case.py")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as fh:
+        fh.write(code)
+    cmd = cmd[:-2] + [path]
+    res = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True, text=True,
+                         timeout=300)
+    sys.stdout.write(res.stdout[-2000:])
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert "status 9" in res.stdout

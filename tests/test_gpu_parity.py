@@ -271,11 +271,7 @@ def test_reupload_without_sort_gives_identical_slots(mc, monkeypatch, with_ids):
     ids = (np.arange(len(xy), dtype=np.int32) * 7 + 3) if with_ids else None
 
     def run(reuploads, sort_only):
-        if sort_only:
-            monkeypatch.setenv("MC2D_UPLOAD_SORT", "1")
-        else:
-            monkeypatch.delenv("MC2D_UPLOAD_SORT", raising=False)
-        with mc.Context(Lx, Ly, 2.5, T=1.0, activity=0.3, delta=0.15, seed=11) as ctx:
+        with mc.Context(Lx, Ly, 2.5, T=1.0, activity=0.3, delta=0.15, seed=11, tuning=dict(upload_sort=int(sort_only))) as ctx:
             ctx.upload(xy, ids)
             first = ctx.info().launches
             for _ in range(reuploads):
@@ -292,7 +288,7 @@ def test_reupload_without_sort_gives_identical_slots(mc, monkeypatch, with_ids):
     assert again < first - 4  # the sort, gather and offset kernels did not run
     for ref in (run(0, False), run(2, True)):
         if ref[1] is not None:
-            assert ref[1] >= first - 1  # MC2D_UPLOAD_SORT=1: the sorted path again
+            assert ref[1] >= first - 1  # tuning.upload_sort = 1: the sorted path again
         assert U0 == ref[2]
         if with_ids:
             assert (d0[0] == ref[3][0]).all() and (d0[1] == ref[3][1]).all()
@@ -519,12 +515,8 @@ def test_batched_items_give_the_same_trajectory(mc, monkeypatch):
     Lx, Ly = 61.0, 47.5
     xy = lattice(48, 38, Lx, Ly, 0.15, 5)  # rho = 0.63: ~40 candidates per cell
     res = []
-    for R in (None, "1"):  # "1" is raised to the minimum, 9 x cell capacity
-        if R is None:
-            monkeypatch.delenv("MC2D_SWEEP_R", raising=False)
-        else:
-            monkeypatch.setenv("MC2D_SWEEP_R", R)
-        with mc.Context(Lx, Ly, 2.5, T=1.2, activity=0.6, delta=0.1, seed=9) as ctx:
+    for R in (0, 1):  # 1 is raised to the minimum, 9 x cell capacity
+        with mc.Context(Lx, Ly, 2.5, T=1.2, activity=0.6, delta=0.1, seed=9, tuning=dict(sweep_slots=R)) as ctx:
             ctx.upload(xy)
             st = ctx.run_sweeps(10, gc_per_cell=2)
             res.append((ctx.download(), st))
@@ -574,12 +566,11 @@ def test_sweep_kernel_variants_are_bit_identical(mc, monkeypatch):
     res = {}
     # "/unfused": one launch per colour pass instead of one per sweep; "/barrier": one launch per sweep with a grid
     # barrier between the colours instead of the per-column-pair completion counters
-    variants = ["0", "4", "8", "4", "2", "4/unfused", "4/barrier"]
+    variants = ["0", "4", "8", "4", "2", "4/unfused", "4/barrier", "4/sepbin", "4/barrier/sepbin"]
     for n, G in enumerate(variants):
-        monkeypatch.setenv("MC2D_SWEEP_G", G.split("/")[0])
-        monkeypatch.setenv("MC2D_SWEEP_FUSE", "0" if "unfused" in G else "1")
-        monkeypatch.setenv("MC2D_SWEEP_PIPELINE", "0" if "barrier" in G else "1")
-        with mc.Context(Lx, Ly, 2.5, T=0.9, activity=0.3, delta=0.12, seed=21) as ctx:
+        tuning = dict(sweep_lanes=int(G.split("/")[0]), fuse_passes=0 if "unfused" in G else 1,
+                      pipeline=0 if "barrier" in G else 1, fuse_rebin=0 if "sepbin" in G else 1)
+        with mc.Context(Lx, Ly, 2.5, T=0.9, activity=0.3, delta=0.12, seed=21, tuning=tuning) as ctx:
             ctx.upload(xy, np.arange(len(xy), dtype=np.int32))
             st = ctx.run_sweeps(12, gc_per_cell=2)
             res[n] = (ctx.download(with_ids=True), st)

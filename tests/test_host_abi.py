@@ -30,7 +30,7 @@ def test_header_and_library_export_the_same_symbols(api):
     L = api.load_library()
     for name in declared:
         assert hasattr(L, name)
-    assert L.mc2d_abi_version() == 1
+    assert L.mc2d_abi_version() == 2
 
 
 def test_library_is_sm100a_only(api):

@@ -7,8 +7,13 @@
 The Philox streams are keyed by the GLOBAL cell id and the colour order / grid shift are pure
 functions of (seed, sweep), so a slab-decomposed run must reproduce the single-GPU trajectory
 BIT FOR BIT (positions, N, counters) and its energy to summation-order accuracy.  Rank 0 runs the
-single-GPU reference on its own device and compares."""
-import math
+single-GPU reference on its own device and compares (bench.slab_bitwise_check — the same check
+bench.py puts into its `parity` object at every N).  Cases: NVT and GCMC; the peer-memory halo and the
+ncclSend/ncclRecv fallback; re-uploads into live storage, with the odd ranks held back after the
+capacity collective when the library was built with -DMC2D_FAULT_INJECTION (MC2D_LIB=.../libmc2d_fi.so);
+a position outside the box on ONE rank must fail the upload on EVERY rank.  tests/test_gpu_multi.py
+runs this file under torchrun when the box has at least two GPUs."""
+import json
 import os
 import sys
 
@@ -17,76 +22,31 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
 import montecarlo_simulation_b200 as m
 from montecarlo_simulation_b200 import api
-
-
-def lattice(n, L, seed):
-    rng = np.random.default_rng(seed)
-    g = np.stack(np.meshgrid(np.arange(n), np.arange(n), indexing="ij"), -1).reshape(-1, 2).astype(float)
-    return (g + 0.5) * (L / n) + rng.uniform(-0.2, 0.2, g.shape)
-
-
-def sort_rows(a):
-    return a[np.lexsort((a[:, 1], a[:, 0]))]
 
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n_side = 227
-    L = 321.0  # int(L/2.5) = 128 cell columns: the same grid for 1, 2, 4 and 8 slabs; rho = 0.5
-    nx1 = api.sweep_grid(L, L, 2.5, 1)[0]
-    nxw = api.sweep_grid(L, L, 2.5, world)[0]
-    assert nx1 == nxw, "pick a box whose cell count is a multiple of 2*world (%d vs %d)" % (nx1, nxw)
-    xy = lattice(n_side, L, 7)
     ok = True
-    for label, kw, plan in (("NVT", dict(activity=0.0), dict(gc_per_cell=0)),
-                            ("GCMC", dict(activity=0.497), dict(gc_per_cell=1))):
-        ctx = m.Context(L, L, 2.5, T=1.0, delta=0.1, seed=11, device=local, rank=rank, nranks=world, **kw)
-        ids = [api.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        ctx.comm_init(ids[0])
-        ctx.upload(xy)  # every rank passes the full set; the library keeps its slab
-        # Re-uploads into live storage (the end-to-end pattern) with the odd ranks held back after the collective:
-        # the neighbours' ghost pushes land before the late rank converts its own cells, which must leave the
-        # ghost columns alone.  NVT pass: direct binning; GCMC pass: the sorted path.
-        os.environ["MC2D_TEST_UPLOAD_LAG_US"] = "3000"
-        if label == "GCMC":
-            os.environ["MC2D_UPLOAD_SORT"] = "1"
-        for _ in range(3):
-            ctx.upload(xy)
-        os.environ.pop("MC2D_TEST_UPLOAD_LAG_US")
-        os.environ.pop("MC2D_UPLOAD_SORT", None)
-        U0, W0, N0 = ctx.total_energy_virial(allreduce=True)
-        st = ctx.run_sweeps(25, **plan)
-        st_all = ctx.allreduce_stats(st)
-        U1, W1, N1 = ctx.total_energy_virial(allreduce=True)
-        mine = ctx.download()
-        sizes = [None] * world
-        dist.all_gather_object(sizes, len(mine))
-        parts = [None] * world
-        dist.all_gather_object(parts, mine)
-        ctx.close()
+    cases = [("NVT", dict(gcmc=False, reuploads=3, tuning=dict(test_upload_lag_us=3000))),
+             ("GCMC", dict(gcmc=True, reuploads=3, tuning=dict(test_upload_lag_us=3000, upload_sort=1))),
+             ("GCMC nccl halo", dict(gcmc=True, tuning=dict(halo_nccl=1))),
+             ("GCMC no overlap", dict(gcmc=True, tuning=dict(halo_overlap=0))),
+             ("GCMC unfused", dict(gcmc=True, tuning=dict(fuse_passes=0)))]
+    for label, kw in cases:
+        res = bench.slab_bitwise_check(m, api, dist, rank, world, local, **kw)
         if rank == 0:
-            allp = np.concatenate(parts)
-            with m.Context(L, L, 2.5, T=1.0, delta=0.1, seed=11, device=local, **kw) as one:
-                one.upload(xy)
-                u0, w0, n0 = one.total_energy_virial()
-                s1 = one.run_sweeps(25, **plan)
-                u1, w1, n1 = one.total_energy_virial()
-                ref = one.download()
-            same_pos = allp.shape == ref.shape and bool((sort_rows(allp) == sort_rows(ref)).all())
-            same_cnt = st_all["attempted"] == s1["attempted"] and st_all["accepted"] == s1["accepted"]
-            rel = lambda a, b: abs(a - b) / max(1.0, abs(b))
-            good = (same_pos and same_cnt and N0 == n0 and N1 == n1 and rel(U0, u0) < 1e-12 and rel(U1, u1) < 1e-12
-                    and rel(W1, w1) < 1e-12 and rel(st_all["energy"], s1["energy"]) < 1e-9)
-            print("%s world=%d: positions bitwise equal=%s counters equal=%s N %d/%d U %.12g/%.12g running %.12g/%.12g -> %s"
-                  % (label, world, same_pos, same_cnt, N1, n1, U1, u1, st_all["energy"], s1["energy"],
-                     "OK" if good else "MISMATCH"), flush=True)
-            ok = ok and good
+            print("%-16s world=%d: %s -> %s" % (label, world, json.dumps(res), "OK" if res["ok"] else "MISMATCH"), flush=True)
+            ok = ok and res["ok"]
     # a position outside the box on ONE rank must fail the upload on EVERY rank (no rank left waiting in a collective)
+    n_side, L = 227, 321.0
+    rng = np.random.default_rng(7)
+    g = np.stack(np.meshgrid(np.arange(n_side), np.arange(n_side), indexing="ij"), -1).reshape(-1, 2).astype(float)
+    xy = (g + 0.5) * (L / n_side) + rng.uniform(-0.2, 0.2, g.shape)
     ctx = m.Context(L, L, 2.5, T=1.0, delta=0.1, seed=11, device=local, rank=rank, nranks=world)
     ids = [api.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
@@ -99,7 +59,7 @@ def main():
             ctx.upload(bad if attempt == 1 else xy)
             raised = False
         except m.MC2DError as e:
-            raised = e.status == 6
+            raised = e.status == api.ERR_OUT_OF_BOX
         want = attempt == 1
         if raised != want:
             print("rank %d: upload attempt %d raised=%s, expected %s" % (rank, attempt, raised, want), flush=True)
