@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 # GPU with tools/calibrate_z.py
 Z_LJ_T1_RHO05 = 0.497
 # the same for WCA (rcut = 2^(1/6), the reference's literal r^2 < 1.2599 test): tools/calibrate_z.py --potential WCA
-Z_WCA_T1_RHO05 = 1.97
+Z_WCA_T1_RHO05 = 10.87
 T_BENCH, RCUT, RHO, DELTA = 1.0, 2.5, 0.5, 0.1
 POTENTIALS = {
     # name -> (rcut, activity, cell_margin): WCA cells of exactly rcut hold 0.63 particles; -1 lets the library widen
@@ -293,8 +293,8 @@ def slab_bitwise_check(m, api, dist, rank, world, local, sweeps=25, gcmc=True, r
     128-column grid is run for `sweeps` GCMC (or NVT) sweeps on `world` slabs — halos, migration through the ghost
     columns, the all-reduced energy — and, on rank 0's GPU, on ONE rank.  The Philox streams are keyed by the GLOBAL cell
     id and the colour order / grid shift are functions of (seed, sweep), so positions and counters must be EQUAL BIT FOR
-    BIT and U, W equal to summation order.  world == 1: the production kernel (k_sweep_p, fused re-bin) against the
-    one-warp-per-cell kernel k_sweep with separate re-bin launches."""
+    BIT and U, W equal to summation order.  world == 1: the production kernel k_sweep_p against the
+    one-warp-per-cell kernel k_sweep."""
     n_side, L = 227, 321.0  # int(321 / 2.5) = 128 cell columns: the same grid for 1, 2, 4 and 8 slabs; rho = 0.5
     rng = np.random.default_rng(7)
     g = np.stack(np.meshgrid(np.arange(n_side), np.arange(n_side), indexing="ij"), -1).reshape(-1, 2).astype(float)
@@ -312,7 +312,7 @@ def slab_bitwise_check(m, api, dist, rank, world, local, sweeps=25, gcmc=True, r
 
     if world == 1:
         a = one_rank(tuning)
-        b = one_rank(dict(sweep_lanes=0, fuse_rebin=0))
+        b = one_rank(dict(sweep_lanes=0))
         got, ref, what = a, b, "k_sweep_p (production) vs k_sweep (one warp per cell), 1 GPU"
         st_all = a["st"]
         allp = a["xy"]

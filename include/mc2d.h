@@ -242,8 +242,6 @@ typedef struct {
     int sweep_warps_per_cta;  /* 0 auto (8) */
     int fuse_passes;          /* 1: the four colour passes of a sweep are ONE cooperative launch; 0: one launch per pass */
     int pipeline;             /* 1: per-column-pair completion counters between the colours; 0: grid barrier */
-    int fuse_rebin;           /* 1: re-bin after the grid shift + work order are phase 0 of the sweep launch (single rank);
-                               * 0: separate k_rebin4 / k_order_local launches */
     int rebin_lanes;          /* 4 (default) or 8 lanes per new cell in the re-bin */
     int energy_unstaged;      /* 1: k_energy_virial_g instead of k_energy_p */
     int halo_nccl;            /* 1: ncclSend/ncclRecv of whole columns instead of stores into the neighbours' memory */
@@ -252,7 +250,7 @@ typedef struct {
     int spin_timeout_ms;      /* budget of every in-kernel wait on a neighbour's flag word; 0 = default (10 000 ms) */
     int test_upload_lag_us;   /* fault injection for tools/check_multi_gpu.py (odd ranks sleep after the capacity collective
                                * of an upload); honoured only by a library built with -DMC2D_FAULT_INJECTION */
-    int reserved[3];
+    int reserved[4];
 } mc2d_tuning;
 int mc2d_get_tuning(mc2d_ctx *ctx, mc2d_tuning *out);
 int mc2d_set_tuning(mc2d_ctx *ctx, const mc2d_tuning *in);

@@ -76,10 +76,10 @@ class Info(C.Structure):
 class Tuning(C.Structure):
     """mc2d_tuning: A-B switches (every variant gives the same trajectory); the library reads no environment"""
     _fields_ = [("sweep_lanes", C.c_int), ("sweep_slots", C.c_int), ("sweep_warps_per_cta", C.c_int),
-                ("fuse_passes", C.c_int), ("pipeline", C.c_int), ("fuse_rebin", C.c_int), ("rebin_lanes", C.c_int),
+                ("fuse_passes", C.c_int), ("pipeline", C.c_int), ("rebin_lanes", C.c_int),
                 ("energy_unstaged", C.c_int), ("halo_nccl", C.c_int), ("halo_overlap", C.c_int),
                 ("upload_sort", C.c_int), ("spin_timeout_ms", C.c_int), ("test_upload_lag_us", C.c_int),
-                ("reserved", C.c_int * 3)]
+                ("reserved", C.c_int * 4)]
 
 
 # every symbol include/mc2d.h declares (tests check the library exports exactly these)

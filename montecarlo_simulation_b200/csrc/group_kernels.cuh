@@ -169,70 +169,14 @@ __global__ void __launch_bounds__(256) k_rebin_g(const double2 *pos_o, const int
     }
 }
 
-// K1', common case: both components of the origin shift exceed the rounding slack and the grid is at least 3
-// cells wide, so exactly the 4 old cells {0, sx} x {0, sy} (sx, sy = sign of the shift) can hold particles of a
-// new cell.  They are scanned in the order k_rebin_g scans them (dx outer, dy inner, ascending): same slots.
+// K1', common case (rebin4_cells, sweep_kernel_p.cuh): exactly 4 old cells can hold particles of a new cell.
 template <int G>
 __global__ void __launch_bounds__(256) k_rebin4(const double2 *pos_o, const int *cnt_o, const int *ids_o,
                                                 double2 *pos_n, int *cnt_n, int *ids_n, Grid gn, int sx, int sy,
                                                 int w0, int n0, int w1, int n1, int *err) {
     constexpr int GPW = 32 / G;
-    const int lane = threadIdx.x & 31;
-    const int gi = lane / G, sl = lane % G;
-    const int wl = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + gi;
-    const bool has = wl < n0 + n1;
-    const int w = wl < n0 ? w0 + wl : w1 + (wl - n0);
-    const int lcx = gn.ghost + (has ? w / gn.ny : 0), cy = has ? w % gn.ny : 0;
-    const int gcx = gn.col0 + (lcx - gn.ghost);
-    const int K = gn.K;
-    const size_t obase = (size_t)(lcx * gn.ny + cy) * K;
-    int tc[4], ts[5];
-    ts[0] = 0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const int ddx = (c >> 1) ? max(sx, 0) : min(sx, 0), ddy = (c & 1) ? max(sy, 0) : min(sy, 0);
-        int ocx = lcx + ddx, ocy = cy + ddy;
-        if (!gn.ghost) {
-            if (ocx < 0) ocx += gn.nx; else if (ocx >= gn.nx) ocx -= gn.nx;
-        }
-        if (ocy < 0) ocy += gn.ny; else if (ocy >= gn.ny) ocy -= gn.ny;
-        tc[c] = ocx * gn.ny + ocy;
-        ts[c + 1] = ts[c] + (has ? cnt_o[tc[c]] : 0);
-    }
-    const int M = ts[4];
-    const int KM = warp_max_int(M);
-    const unsigned gmask = ((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << (gi * G);
-    const unsigned lt = (1u << lane) - 1u;
-    int nout = 0;
-    for (int k0 = 0; k0 < KM; k0 += G) {
-        const int k = k0 + sl;
-        bool take = false;
-        double2 p = make_double2(0.0, 0.0);
-        size_t src = 0;
-        if (k < M) {
-            const int q = (k >= ts[1]) + (k >= ts[2]) + (k >= ts[3]);
-            const int cc = q == 0 ? tc[0] : (q == 1 ? tc[1] : (q == 2 ? tc[2] : tc[3]));
-            const int cs = q == 0 ? 0 : (q == 1 ? ts[1] : (q == 2 ? ts[2] : ts[3]));
-            src = (size_t)cc * K + (k - cs);
-            p = pos_o[src];
-            int ngx, ncy;
-            sweep_cell_of(gn, p.x, p.y, ngx, ncy);
-            take = (ngx == gcx && ncy == cy);
-        }
-        const unsigned m = __ballot_sync(FULL_MASK, take) & gmask;
-        if (take) {
-            const int off = nout + __popc(m & lt);
-            if (off < K) {
-                pos_n[obase + off] = p;
-                if (ids_n) ids_n[obase + off] = ids_o[src];
-            }
-        }
-        nout += __popc(m);
-    }
-    if (has && sl == 0) {
-        cnt_n[lcx * gn.ny + cy] = min(nout, K);
-        if (nout > K) atomicMax(&err[0], nout);
-    }
+    const int wl0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW;
+    rebin4_cells<G>(pos_o, cnt_o, ids_o, pos_n, cnt_n, ids_n, gn, sx, sy, wl0, w0, n0, w1, n1, err);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -339,7 +339,6 @@ static mc2d_tuning default_tuning() {
     t.sweep_lanes = -1;
     t.fuse_passes = 1;
     t.pipeline = 1;
-    t.fuse_rebin = 1;
     t.rebin_lanes = 4;
     t.halo_overlap = 1;
     return t;
@@ -1686,6 +1685,10 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
         CU(cudaGetLastError());
         return MC2D_OK;
     };
+    // single rank / no overlap: the four passes of a sweep go out as ONE cooperative launch (completion counters or a
+    // grid barrier between colours); tuning.fuse_passes = 0 launches them one by one
+    const bool fuse = persistent && !overlap && !g.ghost && ctx->tune.fuse_passes;
+    const size_t sweep_smem = G ? (size_t)R * (sizeof(double2) + (ctx->use_ids ? sizeof(int) : 0)) * wpb : per_warp * wpb;
     for (long long s = 0; s < nsweeps; ++s) {
         int order[4];
         double sx, sy;
@@ -1735,9 +1738,6 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             CU(ctx->done_buf.ensure(sizeof(int) * 4 * (size_t)npairs));
             CU(cudaMemsetAsync(ctx->done_buf.p, 0, sizeof(int) * 4 * (size_t)npairs, ctx->stream));
         }
-        // single rank / no overlap: the four passes of a sweep go out as ONE cooperative launch (grid barrier between
-        // colours); MC2D_SWEEP_FUSE=0 launches them one by one
-        const bool fuse = persistent && !overlap && !g.ghost && ctx->tune.fuse_passes;
         // slab mode: the same single launch, with the halo exchange inside the kernel (boundary items wait on the
         // neighbour's flag word, push their cells into its ghost column, the last one signals)
         const bool fuse_halo = overlap && ctx->tune.fuse_passes && (nitems / npairs) <= ctx->num_sms * wpb;
@@ -1789,7 +1789,7 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             a.trace = trace ? ctx->trace_buf.as<mc2d_trial>() : nullptr;
             a.trace_n = ctx->d_trace_n;
             a.trace_cap = trace_cap;
-            const size_t smem = G ? (size_t)R * (sizeof(double2) + (ctx->use_ids ? sizeof(int) : 0)) * wpb : per_warp * wpb;
+            const size_t smem = sweep_smem;
             const int pot = ctx->prm.potential;
             auto launch_items = [&](const SweepArgs &aa, cudaStream_t st, int reserve) -> int {  // k_sweep_p over aa's column pairs
                 int rc = MC2D_OK;

@@ -39,18 +39,23 @@
 // of the j-th cell of that colour in that column pair, by falling (n_own, n_own + neighbours).
 // Stable counting sort: every rank depends only on the counts, never on timing.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_max_int(int v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(FULL_MASK, v, d));
+    return v;
+}
+
 constexpr int ORDL_NB = 16;  // occupancy bins (15 and above share the first)
 constexpr int ORDL_MB = 8;   // candidate-count bins of width 8 (56 and above share the first)
 constexpr int ORDL_BINS = ORDL_NB * ORDL_MB;
 constexpr int ORDL_WARPS = 4;
 
-// dynamic shared memory: 3 columns x ny counts, then nay packed (bin << 16 | rank in warp)
-__global__ void __launch_bounds__(ORDL_WARPS * 32) k_order_local(Grid g, const int *cnt, int *perm) {
-    extern __shared__ int ol_smem[];
-    __shared__ int wc[ORDL_WARPS][ORDL_BINS];
-    __shared__ int bin_base[ORDL_BINS];
-    constexpr int NT = ORDL_WARPS * 32;
-    const int p = blockIdx.x, colour = blockIdx.y;
+// One (column pair p, colour) task by the NW warps of a CTA (all of its threads call this).
+// ol_smem: 3 columns x ny counts, then nay packed (bin << 16 | rank in warp); wc: NW x ORDL_BINS; bin_base: ORDL_BINS.
+template <int NW>
+__device__ __forceinline__ void order_local_task(const Grid &g, const int *cnt, int *perm, int p, int colour,
+                                                 int *ol_smem, int *wc, int *bin_base) {
+    constexpr int NT = NW * 32;
     const int px = colour & 1, py = colour >> 1;
     const int nay = g.ny >> 1, npairs = g.ncol >> 1;
     const int lcx = g.ghost + 2 * p + px;
@@ -60,13 +65,13 @@ __global__ void __launch_bounds__(ORDL_WARPS * 32) k_order_local(Grid g, const i
         if (!g.ghost) {
             if (col < 0) col += g.nx; else if (col >= g.nx) col -= g.nx;
         }
-        for (int cy = threadIdx.x; cy < g.ny; cy += NT) ol_cnt[c * g.ny + cy] = cnt[col * g.ny + cy];
+        for (int cy = threadIdx.x; cy < g.ny; cy += NT) ol_cnt[c * g.ny + cy] = __ldcg(&cnt[col * g.ny + cy]);
     }
-    for (int i = threadIdx.x; i < ORDL_WARPS * ORDL_BINS; i += NT) (&wc[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < NW * ORDL_BINS; i += NT) wc[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    const int per_warp = (nay + ORDL_WARPS - 1) / ORDL_WARPS;  // each warp owns a contiguous range of rows (stable order)
+    const int per_warp = (nay + NW - 1) / NW;  // each warp owns a contiguous range of rows (stable order)
     for (int k0 = 0; k0 < per_warp; k0 += 32) {
         const int k = k0 + lane;
         const int acy = wib * per_warp + k;
@@ -83,9 +88,9 @@ __global__ void __launch_bounds__(ORDL_WARPS * 32) k_order_local(Grid g, const i
         const unsigned peers = __match_any_sync(FULL_MASK, b);
         const int r = __popc(peers & lt);
         int prev = 0;
-        if (has) prev = wc[wib][b];
+        if (has) prev = wc[wib * ORDL_BINS + b];
         __syncwarp();
-        if (has && r == 0) wc[wib][b] = prev + __popc(peers);
+        if (has && r == 0) wc[wib * ORDL_BINS + b] = prev + __popc(peers);
         __syncwarp();
         if (has) ol_key[acy] = (b << 16) | (prev + r);
     }
@@ -94,9 +99,9 @@ __global__ void __launch_bounds__(ORDL_WARPS * 32) k_order_local(Grid g, const i
     for (int b = threadIdx.x; b < ORDL_BINS; b += NT) {
         int run = 0;
 #pragma unroll
-        for (int w = 0; w < ORDL_WARPS; ++w) {
-            const int v = wc[w][b];
-            wc[w][b] = run;
+        for (int w = 0; w < NW; ++w) {
+            const int v = wc[w * ORDL_BINS + b];
+            wc[w * ORDL_BINS + b] = run;
             run += v;
         }
         bin_base[b] = run;
@@ -128,8 +133,87 @@ __global__ void __launch_bounds__(ORDL_WARPS * 32) k_order_local(Grid g, const i
         const int acy = wib * per_warp + k;
         if (k < per_warp && acy < nay) {
             const int key = ol_key[acy], b = key >> 16;
-            out[bin_base[b] + wc[wib][b] + (key & 0xffff)] = acy;
+            out[bin_base[b] + wc[wib * ORDL_BINS + b] + (key & 0xffff)] = acy;
         }
+    }
+    __syncthreads();  // the next task of this CTA reuses the scratch
+}
+
+// dynamic shared memory: 3 columns x ny counts, then nay keys
+__global__ void __launch_bounds__(ORDL_WARPS * 32) k_order_local(Grid g, const int *cnt, int *perm) {
+    extern __shared__ int ol_smem[];
+    __shared__ int wc[ORDL_WARPS * ORDL_BINS];
+    __shared__ int bin_base[ORDL_BINS];
+    order_local_task<ORDL_WARPS>(g, cnt, perm, blockIdx.x, blockIdx.y, ol_smem, wc, bin_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1', common case (body of k_rebin4, group_kernels.cuh): both components of
+// the origin shift exceed the rounding slack and the grid is at least 3 cells wide, so exactly the 4 old cells
+// {0, sx} x {0, sy} (sx, sy = sign of the shift) can hold particles of a new cell.  They are scanned in the order
+// k_rebin_g scans them (dx outer, dy inner, ascending): same slots.  A warp handles 32/G consecutive owned cells
+// starting at wl0 (all 32 lanes call this).
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, const int *__restrict__ cnt_o,
+                                             const int *__restrict__ ids_o, double2 *pos_n, int *cnt_n, int *ids_n,
+                                             const Grid &gn, int sx, int sy, int wl0, int w0, int n0, int w1, int n1,
+                                             int *err) {
+    const int lane = threadIdx.x & 31;
+    const int gi = lane / G, sl = lane % G;
+    const int wl = wl0 + gi;
+    const bool has = wl < n0 + n1;
+    const int w = wl < n0 ? w0 + wl : w1 + (wl - n0);
+    const int lcx = gn.ghost + (has ? w / gn.ny : 0), cy = has ? w % gn.ny : 0;
+    const int gcx = gn.col0 + (lcx - gn.ghost);
+    const int K = gn.K;
+    const size_t obase = (size_t)(lcx * gn.ny + cy) * K;
+    int tc[4], ts[5];
+    ts[0] = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int ddx = (c >> 1) ? max(sx, 0) : min(sx, 0), ddy = (c & 1) ? max(sy, 0) : min(sy, 0);
+        int ocx = lcx + ddx, ocy = cy + ddy;
+        if (!gn.ghost) {
+            if (ocx < 0) ocx += gn.nx; else if (ocx >= gn.nx) ocx -= gn.nx;
+        }
+        if (ocy < 0) ocy += gn.ny; else if (ocy >= gn.ny) ocy -= gn.ny;
+        tc[c] = ocx * gn.ny + ocy;
+        ts[c + 1] = ts[c] + (has ? cnt_o[tc[c]] : 0);
+    }
+    const int M = ts[4];
+    const int KM = warp_max_int(M);
+    const unsigned gmask = ((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << (gi * G);
+    const unsigned lt = (1u << lane) - 1u;
+    int nout = 0;
+    for (int k0 = 0; k0 < KM; k0 += G) {
+        const int k = k0 + sl;
+        bool take = false;
+        double2 p = make_double2(0.0, 0.0);
+        size_t src = 0;
+        if (k < M) {
+            const int q = (k >= ts[1]) + (k >= ts[2]) + (k >= ts[3]);
+            const int cc = q == 0 ? tc[0] : (q == 1 ? tc[1] : (q == 2 ? tc[2] : tc[3]));
+            const int cs = q == 0 ? 0 : (q == 1 ? ts[1] : (q == 2 ? ts[2] : ts[3]));
+            src = (size_t)cc * K + (k - cs);
+            p = pos_o[src];
+            int ngx, ncy;
+            sweep_cell_of(gn, p.x, p.y, ngx, ncy);
+            take = (ngx == gcx && ncy == cy);
+        }
+        const unsigned m = __ballot_sync(FULL_MASK, take) & gmask;
+        if (take) {
+            const int off = nout + __popc(m & lt);
+            if (off < K) {
+                pos_n[obase + off] = p;
+                if (ids_n) ids_n[obase + off] = ids_o[src];
+            }
+        }
+        nout += __popc(m);
+    }
+    if (has && sl == 0) {
+        cnt_n[lcx * gn.ny + cy] = min(nout, K);
+        if (nout > K) atomicMax(&err[0], nout);
     }
 }
 
@@ -148,14 +232,10 @@ __device__ __forceinline__ double group_sum(double v) {
     for (int d = G / 2; d > 0; d >>= 1) v += __shfl_xor_sync(FULL_MASK, v, d);
     return v;
 }
-__device__ __forceinline__ int warp_max_int(int v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(FULL_MASK, v, d));
-    return v;
-}
 
+// (unrolling the candidate loops does not pay: 49.2 us per colour pass of config #4 without, 50.3 us x2, 54.0 us x4)
 #ifndef MC2D_HOT_UNROLL
-#define MC2D_HOT_UNROLL 2
+#define MC2D_HOT_UNROLL 1
 #endif
 #define MC2D_PRAGMA_(x) _Pragma(#x)
 #define MC2D_UNROLL(n) MC2D_PRAGMA_(unroll n)
@@ -217,15 +297,37 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // leaves ~1e-12 per reciprocal (worst per-trial dE error measured against the oracle: 7e-12 of max(1, |dE|),
 // tools/check_dE_accuracy.py); two steps reach the last bit (worst 1e-15) and cost two more DFMA per pair.
 // The parity hooks K4/K6 keep the IEEE division of the reference.
+// MC2D_SWEEPP_NEWTON = 3 (default): ONE second-order step, r = r0 (1 + e + e^2) with e = 1 - x r0: the error is e^3
+// (~2^-60 for the ~20-bit seed), the same last-bit accuracy as two Newton steps for three DFMA instead of four.
 #ifndef MC2D_SWEEPP_NEWTON
-#define MC2D_SWEEPP_NEWTON 2
+#define MC2D_SWEEPP_NEWTON 3
 #endif
 __device__ __forceinline__ double rcp_newton1(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#if MC2D_SWEEPP_NEWTON == 3
+    const double e = fma(-x, r, 1.0);
+    r = fma(r, fma(e, e, e), r);
+#else
 #pragma unroll
     for (int it = 0; it < MC2D_SWEEPP_NEWTON; ++it) r = fma(r, fma(-x, r, 1.0), r);
+#endif
     return r;
+}
+
+// shared-memory accesses by 32-bit shared-window address: the hot loops keep ONE address register per array instead of
+// re-deriving generic pointers from the kernel arguments (what the compiler did under register pressure)
+__device__ __forceinline__ double2 lds_d2(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_d2(unsigned addr, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ unsigned pin_u32(unsigned v) {  // opaque to the optimiser: the value stays in a register
+    asm volatile("" : "+r"(v));
+    return v;
 }
 
 // Empty candidate slots hold this point: its distance to anything in a cell is ~1e150, beyond every
@@ -543,8 +645,24 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                 acy1 = load_perm(it1, ps, ps1, acx1, rank1);
                 have_it1 = true;
             }
-            // to cell-local coordinates, in place
-            for (int k = sl; k < Ms + n_own; k += G) cand[k] = to_local(cand[k], x_lo, y_lo, g, hLx, hLy);
+            // to cell-local coordinates, in place.  Only a cell on the rim of the periodic box (or of the shifted grid) can
+            // see a periodic image: everywhere else the conversion is two exact subtractions (the same arithmetic).
+            const unsigned cand_s = pin_u32((unsigned)__cvta_generic_to_shared(cand));
+            const unsigned own_s = cand_s + 16u * (unsigned)Ms;
+            {
+                // (rim: the cell or one of its neighbours wraps — column 0 looks back at column nx-1, columns nx-2 and
+                // nx-1 see the cell that the grid shift pushes across the box edge; likewise for rows)
+                const bool rim = has_cell && (gcx == 0 || gcx >= g.nx - 2 || cy == 0 || cy >= g.ny - 2);
+                const unsigned pe = own_s + 16u * (unsigned)n_own;
+                if (__any_sync(FULL_MASK, rim)) {
+                    for (unsigned q = cand_s + 16u * sl; q < pe; q += 16u * G) sts_d2(q, to_local(lds_d2(q), x_lo, y_lo, g, hLx, hLy));
+                } else {
+                    for (unsigned q = cand_s + 16u * sl; q < pe; q += 16u * G) {
+                        const double2 v = lds_d2(q);
+                        sts_d2(q, make_double2(v.x - x_lo, v.y - y_lo));
+                    }
+                }
+            }
             __syncwarp();
 
             bool dirty = false;
@@ -566,7 +684,8 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                     const double Et = __shfl_sync(FULL_MASK, batchE, src);
                     const bool act = t < n_disp;
                     const int i = act ? (int)__umulhi(rx, (uint32_t)n_own) : 0;
-                    const double2 uo = act ? own[i] : make_double2(0.0, 0.0);
+                    const unsigned self_s = own_s + 16u * (unsigned)i;
+                    const double2 uo = act ? lds_d2(self_s) : make_double2(0.0, 0.0);
                     double2 un;
                     un.x = uo.x + a.delta * (2.0 * mc2d_u01(ry) - 1.0);
                     un.y = uo.y + a.delta * (2.0 * mc2d_u01(rz) - 1.0);
@@ -574,20 +693,27 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                     double dE = 0.0;
                     if (POT != POT_IDEAL) {
                         double acc = 0.0;
-                        const int self = Ms + i;
-                        const int ntot = inside ? Ms + n_own : 0;  // a trial that left the cell is rejected unseen
-                        // hot loop: shared memory only; every group runs over its own list
+                        // hot loop: shared memory only; every group runs over its own list, lane sl takes candidates
+                        // sl, sl + G, ...: first the frozen neighbours (no self test), then the cell's own particles.
+                        // A trial that left the cell is rejected unseen (empty ranges).
+                        unsigned q = cand_s + 16u * sl;
+                        const unsigned qn = inside ? own_s : q, qe = inside ? own_s + 16u * (unsigned)n_own : q;
                         MC2D_UNROLL(MC2D_HOT_UNROLL)
-                        for (int k = sl; k < ntot; k += G) {
-                            const double2 c = cand[k];
-                            const bool notself = k != self;
+                        for (; q < qn; q += 16u * G) {
+                            const double2 c = lds_d2(q);
+                            acc += pair_term<POT>(c.x - un.x, c.y - un.y, a.r2cut, a.pp, true) -
+                                   pair_term<POT>(c.x - uo.x, c.y - uo.y, a.r2cut, a.pp, true);
+                        }
+                        for (; q < qe; q += 16u * G) {
+                            const double2 c = lds_d2(q);
+                            const bool notself = q != self_s;
                             acc += pair_term<POT>(c.x - un.x, c.y - un.y, a.r2cut, a.pp, notself) -
                                    pair_term<POT>(c.x - uo.x, c.y - uo.y, a.r2cut, a.pp, notself);
                         }
                         dE = escale * group_sum<G>(acc);
                     }
                     const bool accept = inside && (a.beta * dE < Et);  // MC.cpp:110-115, log form (sweep_kernel.cuh)
-                    if (accept && sl == 0) own[i] = un;
+                    if (accept && sl == 0) sts_d2(self_s, un);
                     if (sl == 0) {
                         c_att[0] += act;
                         c_acc[0] += accept;
@@ -643,16 +769,22 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                     pt.y = mc2d_u01(rz) * g.dy;
                     if (pt.x >= g.dx) pt.x = 0.0;
                     if (pt.y >= g.dy) pt.y = 0.0;
-                    const double2 old = (kind == 2 && n_own > 0) ? own[i] : make_double2(0.0, 0.0);
+                    const unsigned self_s = (kind == 2) ? own_s + 16u * (unsigned)i : 0u;
+                    const double2 old = (kind == 2 && n_own > 0) ? lds_d2(self_s) : make_double2(0.0, 0.0);
                     const double2 probe = (kind == 1) ? pt : old;
                     double dE = 0.0;
                     if (POT != POT_IDEAL) {
                         double acc = 0.0;
-                        const int self = (kind == 2) ? Ms + i : -1;
-                        const int ntot = evaluate ? Ms + n_own : 0;
-                        for (int k = sl; k < ntot; k += G) {
-                            const double2 c = cand[k];
-                            acc += pair_term<POT>(c.x - probe.x, c.y - probe.y, a.r2cut, a.pp, k != self);
+                        unsigned q = cand_s + 16u * sl;
+                        const unsigned qn = evaluate ? own_s : q, qe = evaluate ? own_s + 16u * (unsigned)n_own : q;
+                        MC2D_UNROLL(MC2D_HOT_UNROLL)
+                        for (; q < qn; q += 16u * G) {
+                            const double2 c = lds_d2(q);
+                            acc += pair_term<POT>(c.x - probe.x, c.y - probe.y, a.r2cut, a.pp, true);
+                        }
+                        for (; q < qe; q += 16u * G) {
+                            const double2 c = lds_d2(q);
+                            acc += pair_term<POT>(c.x - probe.x, c.y - probe.y, a.r2cut, a.pp, q != self_s);
                         }
                         acc = escale * group_sum<G>(acc);
                         dE = (kind == 2) ? -acc : acc;  // MC.cpp:200,225
@@ -662,11 +794,11 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                     const bool accept = evaluate && (a.beta * dE - ln_pref < Et);
                     if (sl == 0) {
                         if (accept && kind == 1) {
-                            own[n_own] = pt;
+                            sts_d2(own_s + 16u * (unsigned)n_own, pt);
                             if (a.ids) own_id[n_own] = -1;
                         }
                         if (accept && kind == 2) {
-                            own[i] = own[n_own - 1];
+                            sts_d2(self_s, lds_d2(own_s + 16u * (unsigned)(n_own - 1)));
                             if (a.ids) own_id[i] = own_id[n_own - 1];
                         }
                         c_att[1] += (kind == 1);
@@ -701,7 +833,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
             // ---- write the cell back (absolute coordinates) ----
             if (dirty) {
                 for (int s = sl; s < n_own; s += G) {
-                    const double2 u = own[s];
+                    const double2 u = lds_d2(own_s + 16u * (unsigned)s);
                     double x = x_lo + u.x, y = y_lo + u.y;
                     if (x >= g.Lx) x -= g.Lx; else if (x < 0.0) x += g.Lx;
                     if (y >= g.Ly) y -= g.Ly; else if (y < 0.0) y += g.Ly;

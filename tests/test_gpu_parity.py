@@ -566,10 +566,10 @@ def test_sweep_kernel_variants_are_bit_identical(mc, monkeypatch):
     res = {}
     # "/unfused": one launch per colour pass instead of one per sweep; "/barrier": one launch per sweep with a grid
     # barrier between the colours instead of the per-column-pair completion counters
-    variants = ["0", "4", "8", "4", "2", "4/unfused", "4/barrier", "4/sepbin", "4/barrier/sepbin"]
+    variants = ["0", "4", "8", "4", "2", "4/unfused", "4/barrier"]
     for n, G in enumerate(variants):
         tuning = dict(sweep_lanes=int(G.split("/")[0]), fuse_passes=0 if "unfused" in G else 1,
-                      pipeline=0 if "barrier" in G else 1, fuse_rebin=0 if "sepbin" in G else 1)
+                      pipeline=0 if "barrier" in G else 1)
         with mc.Context(Lx, Ly, 2.5, T=0.9, activity=0.3, delta=0.12, seed=21, tuning=tuning) as ctx:
             ctx.upload(xy, np.arange(len(xy), dtype=np.int32))
             st = ctx.run_sweeps(12, gc_per_cell=2)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""A/B timing of the sweep loop on config #4 (1M particles, GCMC LJ) under environment switches.
-Usage: python tools/ab_sweep.py "MC2D_SWEEP_ORDER=0" "MC2D_SWEEP_ORDER=1 MC2D_SWEEP_G=2" ...
-Each argument is one variant (space-separated NAME=VALUE pairs; "" = defaults).  Every variant
+"""A/B timing of the sweep loop on config #4 (1M particles, GCMC LJ) under tuning switches (mc2d_tuning fields).
+Usage: python tools/ab_sweep.py "" "pipeline=0" "sweep_lanes=2 pipeline=0" ...
+Each argument is one variant (space-separated field=value pairs; "" = defaults).  Every variant
 starts from the same equilibrated configuration and seed, so final N and U must agree between
 variants that only change scheduling."""
 import os, sys
@@ -18,12 +18,9 @@ with m.Context(wl["L"], wl["L"], bench.RCUT, T=bench.T_BENCH, activity=bench.Z_L
     ctx.run_sweeps(200, disp_per_particle=1, gc_per_cell=1)
     start = ctx.download()
 for v in variants:
-    keys = []
-    for kv in v.split():
-        k, val = kv.split("=")
-        os.environ[k] = val
-        keys.append(k)
-    with m.Context(wl["L"], wl["L"], bench.RCUT, T=bench.T_BENCH, activity=bench.Z_LJ_T1_RHO05, delta=bench.DELTA, seed=43) as ctx:
+    tuning = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in v.split()}
+    with m.Context(wl["L"], wl["L"], bench.RCUT, T=bench.T_BENCH, activity=bench.Z_LJ_T1_RHO05, delta=bench.DELTA, seed=43,
+                   tuning=tuning) as ctx:
         ctx.set_kernel_timing(True)
         ctx.upload(start)
         ctx.run_sweeps(3, disp_per_particle=1, gc_per_cell=1)
@@ -41,5 +38,3 @@ for v in variants:
         U, W, N = ctx.total_energy_virial(resync=True)
         print("%-50s %d sweeps: %.3f ms (no per-kernel events: %.3f ms)  k_sweep %.1f us  k_rebin %.1f us  energy %.1f us  N=%d U=%.9f" %
               (v or "(defaults)", sweeps, best[0], untimed, best[1], best[2], ctx.info().last_energy_ms * 1e3, N, U), flush=True)
-    for k in keys:
-        os.environ.pop(k, None)
