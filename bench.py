@@ -319,9 +319,7 @@ def slab_bitwise_check(m, api, dist, rank, world, local, sweeps=25, gcmc=True, r
     else:
         ctx = m.Context(L, L, RCUT, T=T_BENCH, delta=DELTA, seed=11, device=local, rank=rank, nranks=world,
                         tuning=tuning, **kw)
-        ids = [api.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        ctx.comm_init(ids[0])
+        api.bootstrap_comm(ctx, dist)
         ctx.upload(xy)  # every rank passes the full set; the library keeps its slab
         for _ in range(reuploads):  # re-uploads into live storage (the end-to-end pattern)
             ctx.upload(xy)
@@ -427,9 +425,7 @@ def main():
         c = m.Context(Lbox, Lbox, rc, potential=potential, T=T_BENCH, activity=za, delta=DELTA, seed=42, device=local,
                       rank=rk, nranks=nranks, cell_margin=mg if nranks == 1 else 0.0)
         if nranks > 1:
-            ids = [api.comm_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(ids, src=0)
-            c.comm_init(ids[0])
+            api.bootstrap_comm(c, dist)
         return c
 
     def timed_steps(c, nsteps, allreduce, plan):
@@ -578,7 +574,9 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
         ctx.reset_counters()
-        ctx.upload(host[:n_host])  # pinned host -> device, cell build, initial energy
+        # pinned host -> device (chunked, binning overlaps the copy), cell build; no initial-energy pass: the step
+        # re-syncs the energy after its sweeps (mc2d_upload_ex, MC2D_UPLOAD_NO_ENERGY)
+        ctx.upload(host[:n_host], initial_energy=False)
         h2d += 16 * n_host
         st_e = ctx.run_sweeps(S, **plan1)
         Ue, We, Ne = ctx.total_energy_virial(resync=True, allreduce=world > 1)
@@ -590,7 +588,8 @@ def main():
     e2e = {"value": allsum(moves_e2e) / dt, "unit": "moves/s", "h2d_bytes_per_step": h2d // args.e2e_steps,
            "d2h_bytes_per_step": d2h // args.e2e_steps, "steps": args.e2e_steps,
            "ms_per_step": 1e3 * dt / args.e2e_steps, "slot_reallocations": ctx.info().slot_allocs - allocs0,
-           "what": "mc2d_upload(host xy) + %d sweeps + energy/virial + mc2d_download(host xy) per step" % S}
+           "what": "mc2d_upload_ex(host xy, NO_ENERGY) + %d sweeps + energy/virial (resync) + mc2d_download(host xy) per step; "
+                   "copies chunked and overlapped with the binning / compaction kernels" % S}
     halo_mode = ctx.info().halo_mode
     grid_now = [info.nx, info.ny]
     cellcap = info.cell_capacity

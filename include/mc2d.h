@@ -132,6 +132,11 @@ int mc2d_sweep_schedule(uint64_t seed, uint64_t sweep, double cell_dx, double ce
  * cell-offset pass (replaces CellList::build, cell_list.cpp:28-41, and buildInterior,
  * cell_list_parallel.cpp:116-132) and computes the initial energy (MC.cpp:26). */
 int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long long n);
+/* the same with options.  MC2D_UPLOAD_NO_ENERGY: skip the initial-energy pass (MC.cpp:26) — for callers that re-sync the
+ * energy after their sweeps anyway (mc2d_total_energy_virial with resync != 0, the reference's own sampling pattern,
+ * MC.cpp:62-71); until then stats.energy is the SUM OF ACCEPTED dE since this upload, not the total energy. */
+#define MC2D_UPLOAD_NO_ENERGY 1u
+int mc2d_upload_ex(mc2d_ctx *ctx, const double *xy, const int *ids, long long n, unsigned flags);
 /* download: owned particles in cell order; *n_out receives the count (cap = capacity of xy/ids in
  * particles; MC2D_ERR_INVALID if too small).  ids may be NULL.  Particles inserted by GC moves
  * carry id -1. */

@@ -92,7 +92,7 @@ EXPORTS = [
     "mc2d_comm_unique_id", "mc2d_comm_init", "mc2d_allreduce_stats", "mc2d_get_info", "mc2d_get_stream",
     "mc2d_synchronize", "mc2d_set_kernel_timing", "mc2d_calc_neighbor_list", "mc2d_calc_energy_virial_bruteforce",
     "mc2d_rescale_try", "mc2d_rescale_finish", "mc2d_probe_point", "mc2d_probe_particle", "mc2d_apply_probe", "mc2d_measure_fp64_peak",
-    "mc2d_get_tuning", "mc2d_set_tuning",
+    "mc2d_get_tuning", "mc2d_set_tuning", "mc2d_upload_ex",
 ]
 
 _lib = None
@@ -121,6 +121,7 @@ def load_library() -> C.CDLL:
     L.mc2d_halo_route.argtypes = [i, i, i, ip, ip, ip]
     L.mc2d_sweep_schedule.argtypes = [C.c_uint64, C.c_uint64, d, d, i, ip, dp, dp]
     L.mc2d_upload.argtypes = [vp, vp, vp, ll]
+    L.mc2d_upload_ex.argtypes = [vp, vp, vp, ll, C.c_uint]
     L.mc2d_download.argtypes = [vp, vp, vp, ll, C.POINTER(ll)]
     L.mc2d_num_particles.argtypes = [vp, C.POINTER(ll)]
     L.mc2d_run_sweeps.argtypes = [vp, ll, C.POINTER(SweepPlan), C.POINTER(Stats)]
@@ -225,6 +226,14 @@ def comm_unique_id() -> bytes:
     return buf.raw
 
 
+def bootstrap_comm(ctx, dist, src=0):
+    """Multi-GPU bootstrap for torch.distributed hosts: rank `src` creates the 128-byte NCCL unique id, the process group
+    ships it (MPI_Bcast in the reference's world), every rank joins (mc2d_comm_init)."""
+    ids = [comm_unique_id() if dist.get_rank() == src else None]
+    dist.broadcast_object_list(ids, src=src)
+    ctx.comm_init(ids[0])
+
+
 class Context:
     """One GPU context (mc2d_ctx).  Mirrors what MonteCarlo + CellList + ThermodynamicCalculator hold."""
 
@@ -291,13 +300,14 @@ class Context:
         self.close()
 
     # -- particles ------------------------------------------------------------------------------
-    def upload(self, xy, ids=None):
+    def upload(self, xy, ids=None, initial_energy=True):
+        """initial_energy=False: MC2D_UPLOAD_NO_ENERGY (the caller re-syncs the energy after its sweeps)"""
         a, n = self._xy(xy)
         idp = None
         if ids is not None:
             ids = np.ascontiguousarray(ids, dtype=np.int32)
             idp = ids.ctypes.data
-        self._check(self.L.mc2d_upload(self.h, a.ctypes.data, idp, n))
+        self._check(self.L.mc2d_upload_ex(self.h, a.ctypes.data, idp, n, 0 if initial_energy else 1))
 
     def num_particles(self) -> int:
         n = C.c_longlong()

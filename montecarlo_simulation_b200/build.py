@@ -41,6 +41,20 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(tag: str, defines: list) -> str:
+    """A side build for A/B measurements and fault injection: libmc2d_<tag>.so next to the product library (load it with
+    MC2D_LIB=<path>).  `python -m montecarlo_simulation_b200.build --variant fi -DMC2D_FAULT_INJECTION` makes the library
+    tools/check_multi_gpu.py uses to hold odd ranks back inside mc2d_upload; the product build has no such hook."""
+    out = os.path.join(PKG, "libmc2d_%s.so" % tag)
+    cmd = [_nvcc()] + NVCC_FLAGS + list(defines) + ["-I", os.path.join(PKG, "..", "include"), "-o", out] + \
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("nvcc failed building %s" % out)
+    return out
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
@@ -60,4 +74,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build_library(force="--force" in sys.argv, verbose=True))

@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(256) k_halo_sync(HaloArgs h) {
                 *(volatile unsigned long long *)h.dflag[1] = h.seq;
                 __threadfence_system();
             }
-            if (h.wait[0]) spin_until_ge(h.myflag + 0, h.seq, h.err, h.spin_budget_ns);
-            if (h.wait[1]) spin_until_ge(h.myflag + 1, h.seq, h.err, h.spin_budget_ns);
+            if (h.wait[0]) spin_until_ge(h.myflag + 0, h.seq, h.err, h.spin_budget_ns, 4000);
+            if (h.wait[1]) spin_until_ge(h.myflag + 1, h.seq, h.err, h.spin_budget_ns, 4001);
             __threadfence_system();
         }
     }

@@ -11,7 +11,6 @@
 
 #include <algorithm>
 #include <map>
-#include <cub/cub.cuh>
 #include <string>
 #include <vector>
 
@@ -103,6 +102,7 @@ struct PinnedScalars {
     int flags[4];
     int errv[8];
     int maxcount, ovf, csr_kept, pad;
+    int chunk_off[8];
     unsigned long long kept, count, tn;
     unsigned long long ps[2];
     unsigned long long counters[8];
@@ -124,6 +124,7 @@ struct mc2d_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream_b = nullptr;  // slab boundary work (boundary kernels + halo pushes) next to the interior kernels
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};  // copy / kernel pipelining of upload and download
     std::string err;
 
     Grid g{};
@@ -166,7 +167,7 @@ struct mc2d_ctx {
     bool order_valid = false;
     int *d_work = nullptr;  // work-item ticket counters: [p] interior / whole pass p of a sweep, [4 + p] slab boundary
     int num_sms = 0;
-    DevBuf xy_in, ids_in, keys, keys_sorted, idx, idx_sorted, spos, sids, start, cub_tmp, pts, excl, outE, outC,
+    DevBuf xy_in, ids_in, keys, keys_sorted, idx, idx_sorted, spos, sids, start, hist, scan_sums, pts, excl, outE, outC,
         outI, offsets;
     unsigned long long *d_trace_n = nullptr;
 
@@ -398,6 +399,7 @@ extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
     CU(cudaStreamCreateWithFlags(&ctx->stream_b, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
+    for (cudaEvent_t &e : ctx->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
     CU(cudaMalloc(&ctx->d_energy, 4 * sizeof(double)));
     CU(cudaMalloc(&ctx->d_pair_stats, 4 * sizeof(unsigned long long)));
@@ -427,8 +429,8 @@ static int check_peer_timeout(mc2d_ctx *ctx, const int *errv) {
     ctx->have_particles = false;
     FAIL(MC2D_ERR_PEER_TIMEOUT,
          "a neighbour rank did not signal its halo within %d ms (it failed, returned early or died); the slab contexts "
-         "of all ranks are out of step: destroy them",
-         ctx->tune.spin_timeout_ms > 0 ? ctx->tune.spin_timeout_ms : 10000);
+         "of all ranks are out of step: destroy them [first wait to give up: code %d, detail %d]",
+         ctx->tune.spin_timeout_ms > 0 ? ctx->tune.spin_timeout_ms : 10000, errv[6], errv[7]);
 }
 
 static void close_peers(mc2d_ctx *ctx) {
@@ -461,7 +463,7 @@ extern "C" int mc2d_destroy(mc2d_ctx *ctx) {
 #endif
         free_slots(ctx);
         DevBuf *bufs[] = {&ctx->partial, &ctx->trace_buf, &ctx->xy_in, &ctx->ids_in, &ctx->keys, &ctx->keys_sorted,
-                          &ctx->idx, &ctx->idx_sorted, &ctx->spos, &ctx->sids, &ctx->start, &ctx->cub_tmp, &ctx->pts,
+                          &ctx->idx, &ctx->idx_sorted, &ctx->spos, &ctx->sids, &ctx->start, &ctx->hist, &ctx->scan_sums, &ctx->pts,
                           &ctx->excl, &ctx->outE, &ctx->outC, &ctx->outI, &ctx->offsets, &ctx->order_buf, &ctx->done_buf};
         for (DevBuf *b : bufs) b->release();
         if (ctx->d_counters) cudaFree(ctx->d_counters);
@@ -477,6 +479,8 @@ extern "C" int mc2d_destroy(mc2d_ctx *ctx) {
         if (ctx->ev1) cudaEventDestroy(ctx->ev1);
         if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
         if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+        for (cudaEvent_t e : ctx->ev_chunk)
+            if (e) cudaEventDestroy(e);
         if (ctx->stream_b) cudaStreamDestroy(ctx->stream_b);
         for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
         cudaStreamDestroy(ctx->stream);
@@ -486,7 +490,20 @@ extern "C" int mc2d_destroy(mc2d_ctx *ctx) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// CSR build: keys -> radix sort -> gather -> cell offsets   (K1)
+// exclusive scan of n ints: out[0..n) and out[n] = total (own kernels, three launches)
+// ------------------------------------------------------------------------------------------------
+static int exclusive_scan(mc2d_ctx *ctx, const int *in, int n, int *out) {
+    const int nb = std::max(1, (n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    CU(ctx->scan_sums.ensure(sizeof(int) * (size_t)(nb + 1)));
+    k_scan_chunks<<<nb, SCAN_TPB, 0, ctx->stream>>>(in, n, out, ctx->scan_sums.as<int>());
+    k_scan_sums<<<1, SCAN_TPB, 0, ctx->stream>>>(ctx->scan_sums.as<int>(), nb, out + n);
+    k_scan_add<<<nb, SCAN_TPB, 0, ctx->stream>>>(out, n, ctx->scan_sums.as<int>());
+    ctx->launches += 3;
+    return MC2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSR build: keys + histogram -> scan (= cell offsets) -> scatter -> rank inside the bucket + gather   (K1)
 // ------------------------------------------------------------------------------------------------
 // mode 0: reference grid (nx,ny,cdx,cdy given); mode 1: checkerboard grid ctx->g, slab filter.
 // On return ctx->spos / ctx->sids (perm or ids) / ctx->start hold the CSR arrays; *n_kept = number of
@@ -498,41 +515,39 @@ static int build_csr(mc2d_ctx *ctx, const double2 *d_xy, const int *d_ids, long 
     const int nn = (int)n;
     CU(ctx->keys.ensure(sizeof(int) * (size_t)(nn + 1)));
     CU(ctx->keys_sorted.ensure(sizeof(int) * (size_t)(nn + 1)));
-    CU(ctx->idx.ensure(sizeof(int) * (size_t)(nn + 1)));
     CU(ctx->idx_sorted.ensure(sizeof(int) * (size_t)(nn + 1)));
     CU(ctx->spos.ensure(sizeof(double2) * (size_t)(nn + 1)));
     CU(ctx->sids.ensure(sizeof(int) * (size_t)(nn + 1)));
     CU(ctx->start.ensure(sizeof(int) * (size_t)(ncell + 2)));
+    CU(ctx->hist.ensure(sizeof(int) * 2 * (size_t)(ncell + 1)));  // histogram, then the fill counters of the scatter
+    int *hist = ctx->hist.as<int>(), *fill = hist + (ncell + 1);
     CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
+    CU(cudaMemsetAsync(hist, 0, sizeof(int) * 2 * (size_t)(ncell + 1), ctx->stream));
     if (nn > 0) {
         k_cell_keys<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(d_xy, nn, mode, nx, ny, cdx, cdy, ctx->prm.Lx,
-                                                               ctx->prm.Ly, ctx->g, ncell, ctx->keys.as<int>(),
-                                                               ctx->idx.as<int>(), ctx->d_err + 1);
-        ctx->launches++;
-        int end_bit = 1;
-        while ((1LL << end_bit) <= (long long)ncell) ++end_bit;
-        size_t tmp_bytes = 0;
-        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->keys.as<int>(), ctx->keys_sorted.as<int>(),
-                                           ctx->idx.as<int>(), ctx->idx_sorted.as<int>(), nn, 0, end_bit,
-                                           ctx->stream));
-        CU(ctx->cub_tmp.ensure(tmp_bytes));
-        CU(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, ctx->keys.as<int>(), ctx->keys_sorted.as<int>(),
-                                           ctx->idx.as<int>(), ctx->idx_sorted.as<int>(), nn, 0, end_bit,
-                                           ctx->stream));
-        ctx->launches += 3;
-        k_gather_sorted<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(d_xy, d_ids, ctx->idx_sorted.as<int>(), nn,
-                                                                   ctx->spos.as<double2>(), ctx->sids.as<int>());
+                                                               ctx->prm.Ly, ctx->g, ncell, ctx->keys.as<int>(), nullptr,
+                                                               ctx->d_err + 1, hist);
         ctx->launches++;
     }
-    k_cell_bounds<<<(nn + 1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->keys_sorted.as<int>(), nn, ncell,
-                                                                 ctx->start.as<int>());
-    ctx->launches++;
+    // start[c] = first sorted position of cell c; start[ncell] = particles kept (the sentinel bucket follows them)
+    if (int rc = exclusive_scan(ctx, hist, ncell + 1, ctx->start.as<int>())) return rc;
+    if (nn > 0) {
+        k_scatter_keys<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(ctx->keys.as<int>(), nn, ncell, ctx->start.as<int>(), fill,
+                                                                  ctx->idx_sorted.as<int>(), ctx->keys_sorted.as<int>());
+        ctx->launches++;
+    }
     CU(cudaMemcpyAsync(ctx->hp->flags, ctx->d_err, sizeof ctx->hp->flags, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(&ctx->hp->csr_kept, ctx->start.as<int>() + ncell, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
     const int *flags = ctx->hp->flags;
     const int kept = ctx->hp->csr_kept;
+    if (kept > 0) {
+        k_stabilize_gather<<<(kept + 255) / 256, 256, 0, ctx->stream>>>(ctx->idx_sorted.as<int>(), ctx->keys_sorted.as<int>(),
+                                                                      kept, ctx->start.as<int>(), d_xy, d_ids,
+                                                                      ctx->spos.as<double2>(), ctx->sids.as<int>());
+        ctx->launches++;
+    }
     if (bad_out)
         *bad_out = (flags[1] & 1) != 0;
     else if (flags[1] & 1)
@@ -780,11 +795,26 @@ static int choose_capacity(const mc2d_ctx *ctx, int maxcount) {
 static int energy_on_slots(mc2d_ctx *ctx, double *U, double *W, long long *N, bool resync, bool allreduce);
 
 extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long long n) {
-    if (!ctx || (n > 0 && !xy)) return MC2D_ERR_INVALID;
+    return mc2d_upload_ex(ctx, xy, ids, n, 0u);
+}
+
+extern "C" int mc2d_upload_ex(mc2d_ctx *ctx, const double *xy, const int *ids, long long n, unsigned flags_in) {
+    if (!ctx || (n > 0 && !xy) || (flags_in & ~(unsigned)MC2D_UPLOAD_NO_ENERGY)) return MC2D_ERR_INVALID;
     if (!ctx->sweep_ok)
         FAIL(MC2D_ERR_GEOMETRY, "box %g x %g cannot hold an even checkerboard of cells >= rcut=%g (needs >= 2 cells per "
              "direction); only the calculator hooks are available", ctx->prm.Lx, ctx->prm.Ly, ctx->prm.rcut);
-    int rc = h2d_positions(ctx, xy, n);
+    // Slot storage of a fitting capacity exists (every upload but a context's first): the host -> device copy goes out in
+    // chunks on the second stream and k_bin_direct bins a chunk while the next one is still on the bus.
+    const bool pipelined = ctx->arena && ctx->allocK > 0 && ctx->g.K == ctx->allocK && ((ids == nullptr) || ctx->ids[0]) &&
+                           !ctx->tune.upload_sort && !ctx->auto_margin && n >= 4096;
+    int rc = MC2D_OK;
+    if (pipelined) {
+        if (n > 0x7ffffff0LL) FAIL(MC2D_ERR_INVALID, "particle count %lld out of range", n);
+        CU(cudaSetDevice(ctx->dev));
+        CU(ctx->xy_in.ensure(sizeof(double2) * (size_t)(n + 1)));
+    } else {
+        rc = h2d_positions(ctx, xy, n);
+    }
     if (rc) return rc;
     ctx->use_ids = (ids != nullptr);
     if (ids) {
@@ -830,6 +860,36 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
     // computed from the global maximum below.
     bool direct = ctx->arena && ctx->allocK > 0 && g.K == ctx->allocK && (!ctx->use_ids || ctx->ids[0]) &&
                   !ctx->tune.upload_sort;
+    if (!direct && !ctx->tune.upload_sort) {
+        // No fitting slot storage yet (the first upload of a context): count the particles per cell (the histogram pass
+        // of the key sort), agree on the capacity, allocate — and then bin directly like every later upload.
+        const int nn = (int)n;
+        CU(ctx->keys.ensure(sizeof(int) * (size_t)(nn + 1)));
+        CU(ctx->hist.ensure(sizeof(int) * 2 * (size_t)(ncell + 1)));
+        CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
+        CU(cudaMemsetAsync(ctx->hist.p, 0, sizeof(int) * (size_t)(ncell + 1), ctx->stream));
+        if (nn > 0) {
+            k_cell_keys<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(ctx->xy_in.as<double2>(), nn, 1, g.nx, g.ny, g.dx, g.dy,
+                                                                   ctx->prm.Lx, ctx->prm.Ly, g, ncell, ctx->keys.as<int>(),
+                                                                   nullptr, ctx->d_err + 1, ctx->hist.as<int>());
+            k_max_int<<<(ncell + 255) / 256, 256, 0, ctx->stream>>>(ctx->hist.as<int>(), ncell, ctx->d_err + 2);
+            ctx->launches += 2;
+        }
+        CU(cudaMemcpyAsync(ctx->hp->flags, ctx->d_err, sizeof ctx->hp->flags, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaGetLastError());
+        int mc0 = (ctx->hp->flags[1] & 1) ? kOutOfBox : ctx->hp->flags[2];
+        if (g.ghost && ctx->have_comm)
+            if ((rc = comm_max_int(ctx, &mc0))) return rc;
+        if (mc0 == kOutOfBox)
+            FAIL(MC2D_ERR_OUT_OF_BOX, "a position is NaN or outside [0,%g] x [0,%g]", ctx->prm.Lx, ctx->prm.Ly);
+        const int K0 = choose_capacity(ctx, mc0);
+        if (K0 > 1024)
+            FAIL(MC2D_ERR_CELL_OVERFLOW, "a cell holds %d particles; capacity %d exceeds the 1024-slot limit", mc0, K0);
+        if (K0 != ctx->allocK || (ctx->use_ids && !ctx->ids[0]))
+            if ((rc = alloc_slots(ctx, K0))) return rc;
+        direct = true;
+    }
     const bool was_direct = direct;
     if (direct) {
         ctx->have_particles = false;  // the spare buffer may be the current one: a failed upload leaves nothing
@@ -842,10 +902,18 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
         CU(cudaMemsetAsync(ctx->cnt[1], 0, sizeof(int) * (size_t)ncell, ctx->stream));
         CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
         CU(cudaMemsetAsync(ctx->d_pair_stats + 2, 0, sizeof(unsigned long long), ctx->stream));
-        if (n > 0) {
-            k_bin_direct<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
-                ctx->xy_in.as<double2>(), (int)n, ctx->prm.Lx, ctx->prm.Ly, g, K, ctx->pos[1], ctx->cnt[1], tag,
-                ctx->d_err, ctx->d_pair_stats + 2);
+        const int nch = pipelined ? 4 : 1;
+        for (int c = 0; c < nch && n > 0; ++c) {
+            const long long i0 = n * c / nch, i1 = n * (c + 1) / nch;
+            if (pipelined) {
+                CU(cudaMemcpyAsync(ctx->xy_in.as<double2>() + i0, xy + 2 * i0, sizeof(double2) * (size_t)(i1 - i0),
+                                   cudaMemcpyHostToDevice, ctx->stream_b));
+                CU(cudaEventRecord(ctx->ev_chunk[c], ctx->stream_b));
+                CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[c], 0));
+            }
+            k_bin_direct<<<(unsigned)((i1 - i0 + 255) / 256), 256, 0, ctx->stream>>>(
+                ctx->xy_in.as<double2>() + i0, (int)(i1 - i0), (int)i0, ctx->prm.Lx, ctx->prm.Ly, g, K, ctx->pos[1], ctx->cnt[1],
+                tag, ctx->d_err, ctx->d_pair_stats + 2);
             ctx->launches++;
         }
         CU(cudaMemcpyAsync(ctx->hp->flags, ctx->d_err, sizeof ctx->hp->flags, cudaMemcpyDeviceToHost, ctx->stream));
@@ -914,7 +982,9 @@ extern "C" int mc2d_upload(mc2d_ctx *ctx, const double *xy, const int *ids, long
         rc = halo_exchange(ctx, ctx->cur, true, true);
         if (rc) return rc;
     }
-    if (!g.ghost || ctx->have_comm) {
+    if (flags_in & MC2D_UPLOAD_NO_ENERGY) {
+        CU(cudaMemsetAsync(ctx->d_energy, 0, sizeof(double), ctx->stream));  // the running energy counts from zero
+    } else if (!g.ghost || ctx->have_comm) {
         double U, W;
         long long N;
         rc = energy_on_slots(ctx, &U, &W, &N, true, false);
@@ -961,29 +1031,45 @@ extern "C" int mc2d_download(mc2d_ctx *ctx, double *xy, int *ids, long long cap,
     CU(cudaSetDevice(ctx->dev));
     const Grid &g = ctx->g;
     const int cell0 = g.ghost * g.ny, ncell = g.ncol * g.ny;
-    CU(ctx->offsets.ensure(sizeof(int) * (size_t)(ncell + 1)));
-    size_t tmp_bytes = 0;
-    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->cnt[ctx->cur] + cell0, ctx->offsets.as<int>(), ncell,
-                                     ctx->stream));
-    CU(ctx->cub_tmp.ensure(tmp_bytes));
-    CU(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->cnt[ctx->cur] + cell0, ctx->offsets.as<int>(),
-                                     ncell, ctx->stream));
-    ctx->launches += 2;
-    long long n = 0;
-    int rc = count_particles(ctx, &n);
+    CU(ctx->offsets.ensure(sizeof(int) * (size_t)(ncell + 2)));
+    int rc = exclusive_scan(ctx, ctx->cnt[ctx->cur] + cell0, ncell, ctx->offsets.as<int>());  // offsets[ncell] = particle count
     if (rc) return rc;
+    // The cells are compacted in four blocks of columns; the device -> host copy of a block runs on the second stream
+    // while the next block is compacted.  The block boundaries (offsets at 1/4, 2/4, 3/4 of the cells) come back with the
+    // particle count in one synchronisation.
+    const int nch = ncell >= 4096 ? 4 : 1;
+    int cb[5];
+    for (int c = 0; c <= nch; ++c) {
+        cb[c] = (int)((long long)ncell * c / nch);
+        CU(cudaMemcpyAsync(&ctx->hp->chunk_off[c], ctx->offsets.as<int>() + cb[c], sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    const long long n = ctx->hp->chunk_off[nch];
+    ctx->n_last = n;
     *n_out = n;
     if (n > cap) FAIL(MC2D_ERR_INVALID, "download needs room for %lld particles, caller gave %lld", n, cap);
     if (n == 0) return MC2D_OK;
     CU(ctx->spos.ensure(sizeof(double2) * (size_t)n));
     CU(ctx->sids.ensure(sizeof(int) * (size_t)n));
-    k_compact<<<(ncell * 4 + 255) / 256, 256, 0, ctx->stream>>>(ctx->pos[ctx->cur], ctx->cnt[ctx->cur],
-                                                        ctx->use_ids ? ctx->ids[ctx->cur] : nullptr,
-                                                        ctx->offsets.as<int>(), cell0, ncell, g.K,
-                                                        ctx->spos.as<double2>(), ids ? ctx->sids.as<int>() : nullptr);
-    ctx->launches++;
-    if (xy) CU(cudaMemcpyAsync(xy, ctx->spos.p, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (ids) CU(cudaMemcpyAsync(ids, ctx->sids.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    for (int c = 0; c < nch; ++c) {
+        const int nc = cb[c + 1] - cb[c];
+        const long long o0 = ctx->hp->chunk_off[c], o1 = ctx->hp->chunk_off[c + 1];
+        if (nc <= 0) continue;
+        k_compact<<<(nc * 4 + 255) / 256, 256, 0, ctx->stream>>>(ctx->pos[ctx->cur], ctx->cnt[ctx->cur],
+                                                             ctx->use_ids ? ctx->ids[ctx->cur] : nullptr,
+                                                             ctx->offsets.as<int>() + cb[c], cell0 + cb[c], nc, g.K,
+                                                             ctx->spos.as<double2>(), ids ? ctx->sids.as<int>() : nullptr);
+        ctx->launches++;
+        if (o1 <= o0) continue;
+        cudaStream_t cs = nch > 1 ? ctx->stream_b : ctx->stream;
+        if (nch > 1) {
+            CU(cudaEventRecord(ctx->ev_chunk[c], ctx->stream));
+            CU(cudaStreamWaitEvent(cs, ctx->ev_chunk[c], 0));
+        }
+        if (xy) CU(cudaMemcpyAsync(xy + 2 * o0, ctx->spos.as<double2>() + o0, sizeof(double2) * (size_t)(o1 - o0), cudaMemcpyDeviceToHost, cs));
+        if (ids) CU(cudaMemcpyAsync(ids + o0, ctx->sids.as<int>() + o0, sizeof(int) * (size_t)(o1 - o0), cudaMemcpyDeviceToHost, cs));
+    }
+    if (nch > 1) CU(cudaStreamSynchronize(ctx->stream_b));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
     return MC2D_OK;
@@ -1223,13 +1309,8 @@ static int probe_common(mc2d_ctx *ctx, int mode, double x, double y, long long i
         long long n = 0;
         if (int rc = count_particles(ctx, &n)) return rc;
         if (index < 0 || index >= n) FAIL(MC2D_ERR_INVALID, "particle index %lld outside [0, %lld)", index, n);
-        CU(ctx->offsets.ensure(sizeof(int) * (size_t)(ncell + 1)));
-        size_t tmp_bytes = 0;
-        CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->cnt[ctx->cur], ctx->offsets.as<int>(), ncell, ctx->stream));
-        CU(ctx->cub_tmp.ensure(tmp_bytes));
-        CU(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->cnt[ctx->cur], ctx->offsets.as<int>(), ncell,
-                                         ctx->stream));
-        ctx->launches += 2;
+        CU(ctx->offsets.ensure(sizeof(int) * (size_t)(ncell + 2)));
+        if (int rc = exclusive_scan(ctx, ctx->cnt[ctx->cur], ncell, ctx->offsets.as<int>())) return rc;
     } else if (!(x >= 0.0 && x < ctx->prm.Lx && y >= 0.0 && y < ctx->prm.Ly)) {
         FAIL(MC2D_ERR_OUT_OF_BOX, "probe point (%g, %g) outside [0, %g) x [0, %g)", x, y, ctx->prm.Lx, ctx->prm.Ly);
     }
@@ -1398,7 +1479,7 @@ extern "C" int mc2d_calc_cell_ids(mc2d_ctx *ctx, const double *xy, long long n, 
     CU(cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream));
     k_cell_keys<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(ctx->xy_in.as<double2>(), nn, 0, nx, ny, cdx, cdy,
                                                            ctx->prm.Lx, ctx->prm.Ly, ctx->g, nx * ny,
-                                                           ctx->keys.as<int>(), ctx->idx.as<int>(), ctx->d_err + 1);
+                                                           ctx->keys.as<int>(), nullptr, ctx->d_err + 1, nullptr);
     ctx->launches++;
     CU(cudaMemcpyAsync(cell_out, ctx->keys.p, sizeof(int) * (size_t)nn, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1735,12 +1816,15 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             if (!ctx->order_valid)
                 if (int rc = build_order(ctx)) return rc;
             CU(cudaMemsetAsync(ctx->d_work, 0, 8 * sizeof(int), ctx->stream));
-            CU(ctx->done_buf.ensure(sizeof(int) * 4 * (size_t)npairs));
-            CU(cudaMemsetAsync(ctx->done_buf.p, 0, sizeof(int) * 4 * (size_t)npairs, ctx->stream));
+            // finished items per (colour pass, column pair) + 8 words of the slab pipeline (edge items per pass, frontier)
+            CU(ctx->done_buf.ensure(sizeof(int) * (4 * (size_t)npairs + 8)));
+            CU(cudaMemsetAsync(ctx->done_buf.p, 0, sizeof(int) * (4 * (size_t)npairs + 8), ctx->stream));
         }
         // slab mode: the same single launch, with the halo exchange inside the kernel (boundary items wait on the
         // neighbour's flag word, push their cells into its ghost column, the last one signals)
-        const bool fuse_halo = overlap && ctx->tune.fuse_passes && (nitems / npairs) <= ctx->num_sms * wpb;
+        // (grid-barrier variant: its slab-edge items must all be first items of a warp; the pipeline has no such limit)
+        const bool fuse_halo = overlap && ctx->tune.fuse_passes &&
+                               (ctx->tune.pipeline || (nitems / npairs) <= ctx->num_sms * wpb);
         for (int p = 0; p < ((fuse || fuse_halo) ? 1 : 4); ++p) {
             SweepArgs a;
             a.pos = ctx->pos[ctx->cur];
@@ -1823,6 +1907,7 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
                 a.myflag = reinterpret_cast<unsigned long long *>(ctx->arena);
                 a.seq_base = ctx->halo_seq;
                 a.halo_fused = 1;
+                a.pipeline = ctx->tune.pipeline ? 1 : 0;
                 ctx->halo_seq += 4;  // one sync point per colour pass, signalled from inside the kernel
                 if ((rc = ktime_begin(ctx, 3))) return rc;
                 if ((rc = launch_items(a, sa, 0))) return rc;

@@ -425,15 +425,17 @@ __global__ void __launch_bounds__(256) k_bruteforce(const double2 *pos, int n, d
 // so the raw index lies in [-1, nx]).  Not a parity hook: the reference grid uses the exact
 // division of cell_list.cpp:103-109 (k_cell_keys mode 0).
 __device__ __forceinline__ void sweep_cell_of(const Grid &g, double x, double y, int &gcx, int &cy) {
-    int ix = (int)floor((x - g.ox) * g.inv_dx), iy = (int)floor((y - g.oy) * g.inv_dy);
+    // cvt.rmi.s32.f64: floor and conversion in one instruction (the same value as (int)floor(v) for |v| < 2^31)
+    int ix = __double2int_rd((x - g.ox) * g.inv_dx), iy = __double2int_rd((y - g.oy) * g.inv_dy);
     if (ix < 0) ix += g.nx; else if (ix >= g.nx) ix -= g.nx;
     if (iy < 0) iy += g.ny; else if (iy >= g.ny) iy -= g.ny;
     gcx = ix;
     cy = iy;
 }
 
+// hist (optional): particles per key, hist[sentinel] = the ones outside this rank's slab (counting sort, below).
 __global__ void k_cell_keys(const double2 *pos, int n, int mode, int nx, int ny, double cdx, double cdy, double Lx,
-                            double Ly, Grid g, int sentinel, int *keys, int *index, int *flags) {
+                            double Ly, Grid g, int sentinel, int *keys, int *index, int *flags, int *hist) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double2 p = pos[i];
@@ -450,26 +452,122 @@ __global__ void k_cell_keys(const double2 *pos, int n, int mode, int nx, int ny,
         key = (lc < g.ncol) ? (lc + g.ghost) * g.ny + cy : sentinel;
     }
     keys[i] = key;
-    index[i] = i;
+    if (index) index[i] = i;
+    if (hist) atomicAdd(&hist[key], 1);
 }
 
-// after the key sort: gather positions (and ids) into sorted order
-__global__ void k_gather_sorted(const double2 *pos, const int *ids, const int *sorted_index, int n, double2 *pos_out,
-                                int *id_out) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    int i = sorted_index[k];
-    pos_out[k] = pos[i];
-    if (id_out) id_out[k] = ids ? ids[i] : i;
+// ---------------------------------------------------------------------------------------------
+// K1 — the key sort as a STABLE COUNTING SORT (keys are cell ids, a dense range): histogram (k_cell_keys) ->
+// exclusive scan = the cell offsets of the CSR layout -> scatter (slot inside the bucket by atomicAdd: arbitrary) ->
+// k_stabilize_gather: every element finds its rank among the input indices of its bucket, which restores the order
+// a stable sort gives (the reference's bucket order = index order, cell_list.cpp:28-41) and gathers the positions.
+// A bucket holds a cell's particles (a handful), so the rank is a short scan; a degenerate grid (one cell holding
+// everything) makes it quadratic in that cell, which only the tiny boxes of the parity hooks ever see.
+// The scan is the usual three launches (2048 elements per CTA -> CTA totals -> one CTA scans the totals -> add).
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_TPB = 256, SCAN_ITEMS = 8, SCAN_CHUNK = SCAN_TPB * SCAN_ITEMS;
+
+// CTA-wide exclusive scan of one int per thread (blockDim = SCAN_TPB); *total = sum (valid in every thread)
+__device__ __forceinline__ int block_exclusive_scan(int v, int *smem /* SCAN_TPB/32 + 1 ints */, int *total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane >= d) incl += t;
+    }
+    __syncthreads();  // smem may still be read by a previous call
+    if (lane == 31) smem[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int x = lane < SCAN_TPB / 32 ? smem[lane] : 0;
+        int xi = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULL_MASK, xi, d);
+            if (lane >= d) xi += t;
+        }
+        if (lane < SCAN_TPB / 32) smem[lane] = xi - x;
+        if (lane == 31) smem[SCAN_TPB / 32] = xi;
+    }
+    __syncthreads();
+    *total = smem[SCAN_TPB / 32];
+    return smem[w] + incl - v;
 }
 
-// cell-offset pass over the sorted keys: start[c] = first sorted position whose key >= c
-__global__ void k_cell_bounds(const int *sorted_keys, int n, int ncell, int *start) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k > n) return;
-    int prev = (k == 0) ? -1 : min(sorted_keys[k - 1], ncell);
-    int cur = (k == n) ? ncell : min(sorted_keys[k], ncell);
-    for (int c = prev + 1; c <= cur; ++c) start[c] = k;
+// out[i] = exclusive scan of in[] inside each chunk of SCAN_CHUNK elements; sums[chunk] = chunk total
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_chunks(const int *in, int n, int *out, int *sums) {
+    __shared__ int sm[SCAN_TPB / 32 + 1];
+    const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        s += v[k];
+    }
+    int total;
+    int run = block_exclusive_scan(s, sm, &total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// one CTA: sums[] -> exclusive scan in place; *grand = the total
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_sums(int *sums, int nb, int *grand) {
+    __shared__ int sm[SCAN_TPB / 32 + 1];
+    int carry = 0;
+    for (int b0 = 0; b0 < nb; b0 += SCAN_TPB) {
+        const int i = b0 + threadIdx.x;
+        const int v = i < nb ? sums[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, sm, &total);
+        if (i < nb) sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *grand = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_add(int *out, int n, const int *sums) {
+    const int add = sums[blockIdx.x];
+    const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) out[base + k] += add;
+}
+
+// element i -> some slot of its bucket (start[key] + arrival order); the sentinel bucket (outside the slab) is skipped
+__global__ void k_scatter_keys(const int *keys, int n, int sentinel, const int *start, int *fill, int *slot_index,
+                               int *slot_key) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int key = keys[i];
+    if (key >= sentinel) return;
+    const int k = start[key] + atomicAdd(&fill[key], 1);
+    slot_index[k] = i;
+    slot_key[k] = key;
+}
+
+// slot k of the scattered array -> its rank among the input indices of its bucket; gathers position and id there
+__global__ void k_stabilize_gather(const int *slot_index, const int *slot_key, int kept, const int *start,
+                                   const double2 *pos, const int *ids, double2 *pos_out, int *id_out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= kept) return;
+    const int key = slot_key[k], b = start[key], e = start[key + 1], t = slot_index[k];
+    int r = 0;
+    for (int j = b; j < e; ++j) r += slot_index[j] < t;
+    pos_out[b + r] = pos[t];
+    if (id_out) id_out[b + r] = ids ? ids[t] : t;
+}
+
+__global__ void k_max_int(const int *v, int n, int *out_max) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int m = (i < n) ? v[i] : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(FULL_MASK, m, d));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out_max, m);
 }
 
 __global__ void k_max_cell_count(const int *start, int ncell, int *out_max) {
@@ -512,7 +610,7 @@ __global__ void k_csr_to_slots(const double2 *spos, const int *sids, const int *
 // which is the order the stable key sort gives: the slot arrays are bit-identical to the sorted path's.
 // flags = ctx->d_err: [1] bit 0 = a position outside the box, [2] = largest cell count seen.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bin_direct(const double2 *xy, int n, double Lx, double Ly, Grid g, int K,
+__global__ void __launch_bounds__(256) k_bin_direct(const double2 *xy, int n, int i0, double Lx, double Ly, Grid g, int K,
                                                     double2 *pos, int *cnt, int *tag, int *flags,
                                                     unsigned long long *kept) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -532,7 +630,7 @@ __global__ void __launch_bounds__(256) k_bin_direct(const double2 *xy, int n, do
             seen = s + 1;
             if (s < K) {
                 pos[(size_t)c * K + s] = p;
-                tag[(size_t)c * K + s] = i;
+                tag[(size_t)c * K + s] = i0 + i;  // index in the caller's array (this launch covers [i0, i0 + n))
             }
         }
     }

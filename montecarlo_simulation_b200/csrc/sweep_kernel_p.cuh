@@ -259,22 +259,27 @@ __device__ __forceinline__ unsigned long long mc2d_globaltimer() {
     return t;
 }
 // one look inside a spin loop: true when the wait must be abandoned (t0 = 0 on the first call)
-__device__ __forceinline__ bool spin_expired(int *err, unsigned long long budget_ns, unsigned long long &t0) {
+// (code, detail: which wait gave up first — err[6], err[7], reported with the failure)
+__device__ __forceinline__ bool spin_expired(int *err, unsigned long long budget_ns, unsigned long long &t0, int code = 0,
+                                             int detail = 0) {
     if (*(volatile int *)&err[4]) return true;
     const unsigned long long now = mc2d_globaltimer();
     if (t0 == 0) t0 = now;
     if (now - t0 > budget_ns) {
-        atomicExch(&err[4], 1);
+        if (atomicExch(&err[4], 1) == 0) {
+            err[6] = code;
+            err[7] = detail;
+        }
         return true;
     }
     return false;
 }
 __device__ __forceinline__ bool spin_until_ge(const unsigned long long *flag, unsigned long long want, int *err,
-                                              unsigned long long budget_ns) {
+                                              unsigned long long budget_ns, int code = 0) {
     const volatile unsigned long long *f = flag;
     unsigned long long t0 = 0;
     while (*f < want) {
-        if (spin_expired(err, budget_ns, t0)) return false;
+        if (spin_expired(err, budget_ns, t0, code, (int)(want - *f))) return false;
         __nanosleep(32);
     }
     return true;
@@ -512,21 +517,43 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
     // pairs p-1, p, p+1: wait until all their items are finished.  ld.acquire.gpu also drops this SM's L1 copies.
     // block = false: one look (used while the current item is still open: it may itself be one of the items the next
     // one waits for, so blocking there would deadlock); block = true: spin (between items only).
+    // Slab (pipeline + halo_fused): the column pairs do not wrap — beyond the slab edge lies the neighbour rank.  The item
+    // of a pass's slab-edge pair (pair 0 when even columns are active, the last pair otherwise) reads the ghost column
+    // that the neighbour's earlier passes wrote and will overwrite the neighbour's ghost copy of its own column, so it
+    // also waits for the neighbour's flag word: seq_base + psv there means "all slab-edge items of my passes < psv are
+    // finished" (the neighbour signals in pass order, see the end of the item loop).
     auto wait_deps = [&](int psv, int p, bool block) {
-        if (!a.pipeline || psv == 0) return true;
-        const int *d = a.done + (psv - 1) * npairs;
-        const int pm = p == 0 ? npairs - 1 : p - 1, pp = p == npairs - 1 ? 0 : p + 1;
+        if (!a.pipeline) return true;
+        const int cpx = colour_of(psv) & 1;
+        const bool edge = a.halo_fused && p == (cpx == 0 ? 0 : npairs - 1);
+        if (psv == 0 && !edge) return true;
+        const int *d = a.done + (psv > 0 ? psv - 1 : 0) * npairs;
+        int pm = p == 0 ? npairs - 1 : p - 1, pp = p == npairs - 1 ? 0 : p + 1;
+        if (a.halo_fused) {
+            pm = max(p - 1, 0);
+            pp = min(p + 1, npairs - 1);
+        }
         unsigned long long t0 = 0;
         for (;;) {
-            int v0, v1, v2;
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v0) : "l"(d + pm) : "memory");
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v1) : "l"(d + p) : "memory");
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v2) : "l"(d + pp) : "memory");
-            if (min(v0, min(v1, v2)) >= ipp) return true;
+            bool ok = true, lok = true;
+            if (psv > 0) {
+                int v0, v1, v2;
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v0) : "l"(d + pm) : "memory");
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v1) : "l"(d + p) : "memory");
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v2) : "l"(d + pp) : "memory");
+                ok = lok = min(v0, min(v1, v2)) >= ipp;
+            }
+            if (ok && edge) {
+                unsigned long long f;
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(a.myflag + cpx) : "memory");
+                ok = f >= a.seq_base + (unsigned long long)psv;
+            }
+            if (ok) return true;
             if (!block) return false;
             // bounded: these counters are written by this kernel only, so the budget can only run out on a bug or
             // after another wait has already given up; the host then reports the failure instead of hanging
-            if (spin_expired(a.err, a.spin_budget_ns, t0)) return true;
+            // (code 1000 + 100 pass + 10 [local counters were complete] + [slab-edge item]; detail = column pair)
+            if (spin_expired(a.err, a.spin_budget_ns, t0, 1000 + 100 * psv + (lok ? 10 : 0) + (edge ? 1 : 0), p)) return true;
             __nanosleep(64);
         }
     };
@@ -542,7 +569,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
     set_pass(ps);
     work = a.work + ps;
     bpair = (px == 0) ? 0 : npairs - 1;   // even columns active: the first owned column is the one at the slab edge
-    const int hside = (px == 0) ? 0 : 1;  // ... it reads the left ghost and is pushed to the left neighbour
+    int hside = (px == 0) ? 0 : 1;        // ... it reads the left ghost and is pushed to the left neighbour
     int it0 = blockIdx.x * wpb + wib;
     int acx = 0, it0_rank = 0, ps0 = ps;  // column pair of the current item, its rank inside the pair, its colour pass
     const int acy0 = load_perm(it0, ps, ps0, acx, it0_rank);  // the order does not change during a sweep: fetched before the barrier
@@ -553,13 +580,13 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
 #ifdef MC2D_PROFILE_WAIT
     prof_bar += clock64() - pb0;
 #endif
-    if (a.halo_fused && it0 < ipp) {  // boundary item: wait until the neighbour has completed the ghost column it reads
-        if (lane == 0) spin_until_ge(a.myflag + hside, a.seq_base + (unsigned long long)ps, a.err, a.spin_budget_ns);
+    if (a.halo_fused && !a.pipeline && it0 < ipp) {  // boundary item: wait until the neighbour has completed the ghost column it reads
+        if (lane == 0) spin_until_ge(a.myflag + hside, a.seq_base + (unsigned long long)ps, a.err, a.spin_budget_ns, 2000 + ps);
         __syncwarp();
         __threadfence();
     }
     wait_deps(ps0, acx, true);  // (pipeline: the first item of a warp belongs to the first colour unless the grid is tiny)
-    ItemMeta m0 = load_counts(ps0, acx, acy0, a.halo_fused && it0 < ipp);
+    ItemMeta m0 = load_counts(ps0, acx, acy0, a.halo_fused && !a.pipeline && it0 < ipp);
 
     while (it0 < n_all) {
         if (a.pipeline) set_pass(ps0);
@@ -569,7 +596,9 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         bool have_it1 = false, have_m1 = false;
 
         const bool has_cell = m0.acy >= 0;
-        const bool bitem = a.halo_fused && it0 < ipp;  // item of the slab-edge column pair (warp uniform)
+        if (a.pipeline) hside = (px == 0) ? 0 : 1;
+        // item of the slab-edge column pair (warp uniform): barrier mode lists them first, the pipeline by pair
+        const bool bitem = a.halo_fused && (a.pipeline ? acx == (px == 0 ? 0 : npairs - 1) : it0 < ipp);
         const int lcx = g.ghost + 2 * acx + px, cy = 2 * max(m0.acy, 0) + py, gcx = g.col0 + 2 * acx + px;
         const int cell = lcx * g.ny + cy;
         const uint32_t cell_gid = (uint32_t)(gcx * g.ny + cy);
@@ -860,19 +889,56 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
             __threadfence();
             __syncwarp();
             if (lane == 0) atomicAdd(&a.done[ps0 * npairs + acx], 1);
-            if (!have_m1) {
-#ifdef MC2D_PROFILE_WAIT
-                const long long pd0 = clock64();
-#endif
-                wait_deps(ps1, acx1, true);
-#ifdef MC2D_PROFILE_WAIT
-                prof_bar += clock64() - pd0;
-#endif
-                m1 = load_counts(ps1, acx1, acy1, false);
-                have_m1 = true;
-            }
         }
-        if (bitem) {  // one more boundary item done; the last one signals both neighbours
+        if (bitem && a.pipeline) {
+            // One more slab-edge item of pass ps0 done.  Signals go out in PASS ORDER: the flag value seq_base + f + 1
+            // promises that the slab-edge items of ALL passes <= f are finished — they have read the ghost column (the
+            // neighbour may overwrite it) and pushed their cells (the neighbour may read them).  Without a grid barrier
+            // the edge items of pass f + 1 can finish before those of pass f, so whoever completes a pass takes a
+            // (local) lock and moves the frontier over every pass that is complete by then; under the lock the plain
+            // stores into the neighbours' flag words stay monotonic (no peer atomics needed).  This happens BEFORE the
+            // warp may block on its next item: that item can depend, through the neighbour, on this very signal.
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) {
+                int *bd = a.done + 4 * npairs;  // [0..3] finished slab-edge items per pass, [4] passes signalled, [5] lock
+                if (atomicAdd(&bd[ps0], 1) == ipp - 1) {
+                    __threadfence();
+                    unsigned long long t0 = 0;
+                    while (atomicCAS(&bd[5], 0, 1) != 0) {
+                        if (spin_expired(a.err, a.spin_budget_ns, t0, 3000 + ps0)) break;
+                        __nanosleep(64);
+                    }
+                    for (;;) {
+                        int f, n = 0;
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(bd + 4) : "memory");
+                        if (f < a.npass) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(n) : "l"(bd + f) : "memory");
+                        if (f >= a.npass || n < ipp) break;  // (whoever completes pass f continues from there)
+                        const unsigned long long seq = a.seq_base + (unsigned long long)f + 1ull;
+                        __threadfence_system();
+                        *(volatile unsigned long long *)a.hflag[0] = seq;
+                        *(volatile unsigned long long *)a.hflag[1] = seq;
+                        __threadfence_system();
+                        atomicExch(&bd[4], f + 1);
+                    }
+                    __threadfence();
+                    atomicExch(&bd[5], 0);
+                }
+            }
+            __syncwarp();
+        }
+        if (a.pipeline && !have_m1) {
+#ifdef MC2D_PROFILE_WAIT
+            const long long pd0 = clock64();
+#endif
+            wait_deps(ps1, acx1, true);
+#ifdef MC2D_PROFILE_WAIT
+            prof_bar += clock64() - pd0;
+#endif
+            m1 = load_counts(ps1, acx1, acy1, false);
+            have_m1 = true;
+        }
+        if (bitem && !a.pipeline) {  // grid-barrier variant: one more boundary item done; the last one signals both neighbours
             __threadfence_system();
             __syncwarp();
             if (lane == 0) {

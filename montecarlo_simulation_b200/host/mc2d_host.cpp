@@ -760,7 +760,10 @@ bool GibbsMonteCarlo::particle_exchange() {
     //   N_F V_T / ((N_T + 1) V_F) exp(-beta dU).
     // GibbsMC.cpp:359,382 has the ratio upside down, V_F (N_T + 1) / (V_T (N_F + 1)): with it an ideal gas
     // collapses into one box.  A reference defect, not copied.
-    const double arg = std::exp(-beta_ * (dU_to + dU_from)) * N_from * T.box.getV() / ((N_to + 1) * F.box.getV());
+    // reference_exchange_ratio = true reproduces the reference's expression for output-parity runs.
+    const double ratio = reference_exchange_ratio ? F.box.getV() * (N_to + 1) / (T.box.getV() * (N_from + 1))
+                                                  : N_from * T.box.getV() / ((N_to + 1) * F.box.getV());
+    const double arg = std::exp(-beta_ * (dU_to + dU_from)) * ratio;
     const bool accept = rng_.uniform01() < arg;
     if (accept) {
         T.gpu->check(mc2d_apply_probe(T.gpu->get(), 1));

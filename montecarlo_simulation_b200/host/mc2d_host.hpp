@@ -266,6 +266,10 @@ public:
     int equlibrateNPT(size_t nSteps, size_t fOutputStep, size_t fUpdateCell);
     int equlibratemuVT(size_t nSteps, size_t fOutputStep, size_t fUpdateCell);
     double w_1 = 0, w_2 = 0;  // Widom accumulators of the exchange move (GibbsMC.cpp:352,375)
+    // false (default): particle exchange accepts with the detailed-balance ratio N_F V_T / ((N_T + 1) V_F);
+    // true: with the reference's own expression V_F (N_T + 1) / (V_T (N_F + 1)) (GibbsMC.cpp:359,382) — for A/B runs
+    // against the reference's output only: with it an ideal gas collapses into one box.
+    bool reference_exchange_ratio = false;
     // state, for tests and drivers
     const SimulationBox &getBox(int which) const;
     long long getNumParticles(int which) const;

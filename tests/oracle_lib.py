@@ -344,6 +344,8 @@ class Ref:
             L.ref_mc_set_delta_V.argtypes = [C.c_void_p, d]
             L.ref_mc_volume.restype = d
             L.ref_mc_volume.argtypes = [C.c_void_p]
+        if hasattr(L, "ref_mc_run_exact"):
+            L.ref_mc_run_exact.argtypes = [C.c_void_p, C.c_size_t, i, c_double_p]
         L.ref_time_mc_run.restype = d
         L.ref_time_mc_run.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, c_ll_p]
         L.ref_time_moves.restype = d
@@ -405,6 +407,12 @@ class Ref:
            delta=0.1, ensemble=NVT, seed=1):
         return _MC(self.lib, "ref_", Lx, Ly, xy, delta=delta, ensemble=ensemble, seed=seed,
                    ref_args=(T, press, ptype, rcut, mu, f, alpha, A0, kappa))
+
+    def run_exact(self, mc: _MC, nsweeps, gcmc):
+        """nsweeps of the reference's moves with an exact neighbour search (ref_shim.cpp: ref_mc_run_exact) -> (N, E)"""
+        e = C.c_double()
+        n = self.lib.ref_mc_run_exact(mc.h, nsweeps, int(gcmc), C.byref(e))
+        return n, e.value
 
     def time_mc_run(self, mc: _MC, nsteps, fupdate):
         moves = C.c_longlong()

@@ -1,8 +1,8 @@
-"""Host-side plumbing of the 1-D slab decomposition over torch.distributed (one process per GPU).
+"""TEST SCAFFOLDING (used by tests/test_slab_gloo.py only): the routing arithmetic of the 1-D slab decomposition
+restated over torch.distributed tensors, so that it can be exercised with the gloo backend on a CPU-only host.
 
-The data path itself (halo columns, migrants, the cross-GPU sum) runs inside libmc2d.so over NCCL;
-this module only bootstraps it and offers the same exchange protocol over torch.distributed
-tensors so that the routing logic can be exercised with the gloo backend on CPU.
+The data path itself (halo columns, migrants, the cross-GPU sum) runs inside libmc2d.so over NVLink peer memory /
+NCCL and is tested on GPUs by tests/test_gpu_multi.py and bench.py's `parity` object; nothing here is product code.
 
 Replaces: mpi_src/simulatin_box.cpp Decomposition (Px = nranks, Py = 1), the neighbour bookkeeping
 of mpi_src/particle_exchange.cpp:96-112, and bcast_seed_ (MC_parallel.cpp:218-230; not needed: the
@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import api
+from montecarlo_simulation_b200 import api
 
 
 def slab_of_x(x, Lx, Ly, rcut, nranks):
@@ -27,13 +27,6 @@ def partition(xy, Lx, Ly, rcut, nranks, rank):
     """the particles rank `rank` owns (every particle belongs to exactly one rank)."""
     xy = np.asarray(xy, dtype=np.float64).reshape(-1, 2)
     return xy[slab_of_x(xy[:, 0], Lx, Ly, rcut, nranks) == rank]
-
-
-def bootstrap_comm(ctx: "api.Context", dist, src=0):
-    """rank `src` creates the NCCL unique id, torch.distributed ships it, every rank joins."""
-    ids = [api.comm_unique_id() if dist.get_rank() == src else None]
-    dist.broadcast_object_list(ids, src=src)
-    ctx.comm_init(ids[0])
 
 
 def exchange_columns(dist, colour, first_col, last_col):

@@ -262,8 +262,9 @@ def test_upload_download_roundtrip_and_slot_energy(mc, oracle, Lx, Ly, nx, ny):
 
 @pytest.mark.parametrize("with_ids", [True, False])
 def test_reupload_without_sort_gives_identical_slots(mc, monkeypatch, with_ids):
-    """A second upload into existing slot storage bins directly (k_bin_direct + k_order_cells, no key sort).  The slot
-    arrays must be bit-identical to the sorted path's: same download order, same ids, same trajectory afterwards."""
+    """Uploads bin directly (k_bin_direct + k_order_cells; the first one counts first to size the storage).  The slot
+    arrays must be bit-identical to those of the key-sort path (tuning.upload_sort: counting sort -> CSR -> slots): same
+    download order, same ids, same trajectory afterwards."""
     Lx = Ly = 61.0
     rng = np.random.default_rng(5)
     xy = lattice(48, 40, Lx, Ly, 0.3, 7)
@@ -285,7 +286,7 @@ def test_reupload_without_sort_gives_identical_slots(mc, monkeypatch, with_ids):
             return first, (again if reuploads else None), U0, d0, st, d1
 
     first, again, U0, d0, st, d1 = run(2, False)
-    assert again < first - 4  # the sort, gather and offset kernels did not run
+    assert again == first - 2  # a re-upload skips the count pass (keys + max) that sized the storage: no sort anywhere
     for ref in (run(0, False), run(2, True)):
         if ref[1] is not None:
             assert ref[1] >= first - 1  # tuning.upload_sort = 1: the sorted path again
@@ -785,3 +786,29 @@ def test_single_particle_probes_match_oracle(mc, oracle):
             ctx.probe_particle(len(final))
         st = ctx.run_sweeps(3)
         assert relerr(st["energy"], oracle.total_energy_celllist(calc, Lx, Ly, ctx.download())) < 1e-9
+
+
+def test_pipelined_reupload_and_no_energy_option(mc):
+    """Every upload but a context's first copies host -> device in chunks that k_bin_direct bins while the next chunk is
+    on the bus, and mc2d_download copies block-wise behind k_compact: same slots, same order, ids intact.
+    MC2D_UPLOAD_NO_ENERGY skips the initial-energy pass: the running energy then counts accepted dE from zero."""
+    Lx = Ly = 230.0
+    xy = lattice(160, 160, Lx, Ly, 0.3, 17)
+    rng = np.random.default_rng(3)
+    xy = xy[rng.permutation(len(xy))]
+    ids = np.arange(len(xy), dtype=np.int32)[::-1].copy()
+    with mc.Context(Lx, Ly, 2.5, T=1.0, activity=0.2, delta=0.1, seed=5) as ctx:
+        ctx.upload(xy, ids)                       # first upload: count, allocate, bin
+        d0, i0 = ctx.download(with_ids=True)
+        U0 = ctx.total_energy_virial()[0]
+        ctx.upload(xy, ids)                       # re-upload: chunked copy + binning
+        d1, i1 = ctx.download(with_ids=True)
+        assert (d0 == d1).all() and (i0 == i1).all()
+        assert (xy[len(xy) - 1 - i1] == d1).all()  # ids travel with their particle
+        assert ctx.stats()["energy"] == U0
+        ctx.upload(xy, ids, initial_energy=False)
+        assert ctx.stats()["energy"] == 0.0
+        st = ctx.run_sweeps(4, gc_per_cell=1)
+        U1 = ctx.total_energy_virial(resync=True)[0]
+        assert abs(st["energy"] - (U1 - U0)) < 1e-9 * max(1.0, abs(U0))  # sum of accepted dE since the upload
+        assert ctx.stats()["energy"] == U1

@@ -201,3 +201,137 @@ def test_upload_leaves_ghost_columns_to_the_neighbour(n):
         except Violation:
             caught += 1
     assert caught > 30
+
+
+# ---- slab pipeline: no grid barrier between the colour passes (k_sweep_p, pipeline + halo_fused) ------------------------
+# Without the barrier the slab-edge items of a rank's passes form two chains that run concurrently: the items of the
+# FIRST column pair (edge items of the even passes; they read the left ghost) and those of the LAST pair (edge items of
+# the odd passes; right ghost).  Inside a chain the passes stay ordered (an item waits for the previous pass's items of
+# its own pair), between the chains nothing orders them.  The flag value t + 1 must nevertheless mean "every edge item of
+# my sync points <= t is finished", because the neighbour takes it as the licence to overwrite the ghost column I read
+# AND as the promise that the ghost column it reads is complete.  So signals go out in pass order: whoever completes a
+# pass moves a frontier over all passes that are complete by then (max-merge, two warps may signal back to back).  The
+# broken variant signals t + 1 as soon as the edge item of pass t is done — the naive port of the barrier version.
+
+def pipelined_rank(rk, ranks, orders, nsweeps, broken):
+    """-> the generators (threads) of one rank: a sequencer (re-bin, then releases the two chains of the sweep) and
+    the chains themselves are created per sweep by the sequencer."""
+    n = rk.n
+    left, right = ranks[(rk.r - 1) % n], ranks[(rk.r + 1) % n]
+    nb = [left, right]
+    state = {"threads": []}
+
+    def signal(seq):
+        left.flag[1] = max(left.flag[1], seq)
+        right.flag[0] = max(right.flag[0], seq)
+
+    def read(buf, side, t):
+        rk.reading.add((buf, side))
+        yield
+        want = expected_version(orders, t, 1 if side == 0 else 0)
+        if rk.ghost[buf][side] != want:
+            raise Violation("rank %d sync %d: ghost side %d holds version %d, wants %d" % (rk.r, t, side, rk.ghost[buf][side], want))
+        rk.reading.discard((buf, side))
+
+    def push(buf, side):
+        target, tside = nb[side], 1 - side
+        if (buf, tside) in target.reading:
+            raise Violation("rank %d writes ghost %d of rank %d while it is being read" % (rk.r, tside, target.r))
+        target.ghost[buf][tside] = rk.col[side]
+
+    def chain(k, side, done, frontier):
+        s, new = 5 * k, (k + 1) % 2
+        for p in range(4):
+            if ((orders[k][p] & 1) == 0) != (side == 0):
+                continue
+            t = s + 1 + p
+            while rk.flag[side] < t:
+                yield
+            yield from read(new, side, t)
+            rk.col[side] += 1
+            yield
+            push(new, side)
+            yield
+            done[p] = True
+            if broken:
+                signal(t + 1)
+            else:
+                while frontier[0] < 4 and done[frontier[0]]:
+                    frontier[0] += 1
+                    signal(s + 1 + frontier[0])
+            yield
+
+    def sequencer():
+        for k in range(nsweeps):
+            s, old, new = 5 * k, k % 2, (k + 1) % 2
+            for side in (0, 1):
+                while rk.flag[side] < s:
+                    yield
+            yield from read(old, 0, s)
+            yield from read(old, 1, s)
+            rk.col[0] += 1
+            rk.col[1] += 1
+            yield
+            push(new, 0)
+            yield
+            push(new, 1)
+            signal(s + 1)
+            done, frontier = [False] * 4, [0]
+            chains = [chain(k, 0, done, frontier), chain(k, 1, done, frontier)]
+            state["threads"] = chains[:]
+            while state["threads"]:  # the kernel ends when both chains are through
+                yield
+        t = 5 * nsweeps
+        for side in (0, 1):
+            while rk.flag[side] < t:
+                yield
+        yield from read(nsweeps % 2, 0, t)
+        yield from read(nsweeps % 2, 1, t)
+
+    return sequencer(), state
+
+
+def simulate_pipelined(n, nsweeps, seed, broken=False):
+    rng = random.Random(seed)
+    orders = [rng.sample(range(4), 4) for _ in range(nsweeps)]
+    ranks = [Rank(r, n) for r in range(n)]
+    seqs = [pipelined_rank(rk, ranks, orders, nsweeps, broken) for rk in ranks]
+    alive = list(range(n))
+    idle = 0
+    while alive:
+        i = rng.choice(alive) if rng.random() < 0.7 else alive[0]
+        gen, state = seqs[i]
+        before = [(rk.flag[:], rk.col[:]) for rk in ranks]
+        # one step of this rank: one of its chains (a chain is often far ahead of the other) or its sequencer
+        th = state["threads"]
+        try:
+            if th and rng.random() < 0.9:
+                c = th[0] if rng.random() < 0.5 else rng.choice(th)
+                try:
+                    next(c)
+                except StopIteration:
+                    th.remove(c)
+            else:
+                next(gen)
+        except StopIteration:
+            alive.remove(i)
+        idle = idle + 1 if before == [(rk.flag[:], rk.col[:]) for rk in ranks] else 0
+        if idle > 40000:
+            raise Violation("deadlock: no rank makes progress")
+    return True
+
+
+@pytest.mark.parametrize("n", [2, 3, 8])
+def test_pipelined_protocol_signals_in_pass_order(n):
+    for seed in range(300):
+        assert simulate_pipelined(n, nsweeps=4, seed=7000 * n + seed)
+
+
+def test_the_checker_catches_out_of_order_signals():
+    caught = 0
+    for seed in range(300):
+        try:
+            simulate_pipelined(4, nsweeps=4, seed=seed, broken=True)
+        except Violation:
+            caught += 1
+    assert caught > 30

@@ -24,7 +24,8 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from montecarlo_simulation_b200 import api, slab
+    from montecarlo_simulation_b200 import api
+    import slab_routing_model as slab
 
     Lx, Ly, rcut = 321.0, 200.0, 2.5
     xy = np.random.default_rng(5).uniform(0, 1, (20000, 2)) * [Lx, Ly]

@@ -32,12 +32,15 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    cases = [("NVT", dict(gcmc=False, reuploads=3, tuning=dict(test_upload_lag_us=3000))),
+    cases = [("GCMC plain", dict(gcmc=True)),
+             ("NVT", dict(gcmc=False, reuploads=3, tuning=dict(test_upload_lag_us=3000))),
              ("GCMC", dict(gcmc=True, reuploads=3, tuning=dict(test_upload_lag_us=3000, upload_sort=1))),
              ("GCMC nccl halo", dict(gcmc=True, tuning=dict(halo_nccl=1))),
              ("GCMC no overlap", dict(gcmc=True, tuning=dict(halo_overlap=0))),
-             ("GCMC unfused", dict(gcmc=True, tuning=dict(fuse_passes=0)))]
+             ("GCMC unfused", dict(gcmc=True, tuning=dict(fuse_passes=0))),
+             ("GCMC grid barrier", dict(gcmc=True, tuning=dict(pipeline=0)))]
     for label, kw in cases:
+        kw["tuning"] = dict(kw.get("tuning") or {}, spin_timeout_ms=3000)  # a protocol bug shows up as status 9 within seconds
         res = bench.slab_bitwise_check(m, api, dist, rank, world, local, **kw)
         if rank == 0:
             print("%-16s world=%d: %s -> %s" % (label, world, json.dumps(res), "OK" if res["ok"] else "MISMATCH"), flush=True)
