@@ -170,13 +170,13 @@ __global__ void __launch_bounds__(256) k_rebin_g(const double2 *pos_o, const int
 }
 
 // K1', common case (rebin4_cells, sweep_kernel_p.cuh): exactly 4 old cells can hold particles of a new cell.
-template <int G>
-__global__ void __launch_bounds__(256) k_rebin4(const double2 *pos_o, const int *cnt_o, const int *ids_o,
+template <int G, bool HALO>
+__global__ void __launch_bounds__(256, HALO ? 5 : 1) k_rebin4(const double2 *pos_o, const int *cnt_o, const int *ids_o,
                                                 double2 *pos_n, int *cnt_n, int *ids_n, Grid gn, int sx, int sy,
-                                                int w0, int n0, int w1, int n1, int *err) {
+                                                int w0, int n0, int w1, int n1, int *err, SlabHalo sh) {
     constexpr int GPW = 32 / G;
     const int wl0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW;
-    rebin4_cells<G>(pos_o, cnt_o, ids_o, pos_n, cnt_n, ids_n, gn, sx, sy, wl0, w0, n0, w1, n1, err);
+    rebin4_cells<G, HALO>(pos_o, cnt_o, ids_o, pos_n, cnt_n, ids_n, gn, sx, sy, wl0, w0, n0, w1, n1, err, sh);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1125,7 +1125,13 @@ static int item_layout(mc2d_ctx *ctx, ItemLayout *out) {
 }
 
 // per colour and column pair: active cells by falling (occupancy, candidates) -> ctx->order_buf
-static int build_order(mc2d_ctx *ctx) {
+static SlabHalo no_slab_halo() {
+    SlabHalo sh;
+    memset(&sh, 0, sizeof sh);
+    return sh;
+}
+
+static int build_order(mc2d_ctx *ctx, const SlabHalo *wait = nullptr) {
     const Grid &g = ctx->g;
     const int ncell = g.ncol * g.ny;
     const size_t smem = sizeof(int) * (size_t)(3 * g.ny + g.ny / 2);
@@ -1136,7 +1142,8 @@ static int build_order(mc2d_ctx *ctx) {
         ls.occ = 1;
     }
     CU(ctx->order_buf.ensure(sizeof(int) * (size_t)ncell));
-    k_order_local<<<dim3(g.ncol / 2, 4), ORDL_WARPS * 32, smem, ctx->stream>>>(g, ctx->cnt[ctx->cur], ctx->order_buf.as<int>());
+    k_order_local<<<dim3(g.ncol / 2, 4), ORDL_WARPS * 32, smem, ctx->stream>>>(g, ctx->cnt[ctx->cur], ctx->order_buf.as<int>(),
+                                                                                  wait ? *wait : no_slab_halo());
     ctx->launches++;
     ctx->order_valid = true;
     return MC2D_OK;
@@ -1752,8 +1759,8 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
         const int n = n0 + n1;
         const double sdx = gn.ox - go.ox, sdy = gn.oy - go.oy;
         if (K <= 64 && rebin_G == 4 && fabs(sdx) > 1e-9 * gn.dx && fabs(sdy) > 1e-9 * gn.dy && gn.nx >= 3 && gn.ny >= 3)
-            k_rebin4<4><<<(n + 63) / 64, 256, 0, st>>>(po, co, io, ctx->pos[nb], ctx->cnt[nb], in, gn, sdx > 0 ? 1 : -1,
-                                                        sdy > 0 ? 1 : -1, w0, n0, w1, n1, ctx->d_err);
+            k_rebin4<4, false><<<(n + 63) / 64, 256, 0, st>>>(po, co, io, ctx->pos[nb], ctx->cnt[nb], in, gn, sdx > 0 ? 1 : -1,
+                                                        sdy > 0 ? 1 : -1, w0, n0, w1, n1, ctx->d_err, no_slab_halo());
         else if (K <= 64 && rebin_G == 4)  // 4 lanes per new cell, 8 cells per warp
             k_rebin_g<4><<<(n + 63) / 64, 256, 0, st>>>(po, co, io, ctx->pos[nb], ctx->cnt[nb], in, gn, gn.ox - go.ox,
                                                          gn.oy - go.oy, w0, n0, w1, n1, ctx->d_err);
@@ -1770,16 +1777,71 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     // grid barrier between colours); tuning.fuse_passes = 0 launches them one by one
     const bool fuse = persistent && !overlap && !g.ghost && ctx->tune.fuse_passes;
     const size_t sweep_smem = G ? (size_t)R * (sizeof(double2) + (ctx->use_ids ? sizeof(int) : 0)) * wpb : per_warp * wpb;
+    // Slab mode, everything on ONE stream: the re-bin kernel itself waits for the old ghost columns, pushes the
+    // re-binned boundary columns into the neighbours' ghost columns and signals; k_order_local waits for the
+    // neighbours' signal before it reads the new ghost counts; the sweep kernel does the rest (halo_fused + pipeline).
+    // Without the four stream joins and the three side-stream launches per sweep of the two-stream variant (which
+    // stays for the grid-barrier / per-pass A-B variants and for shifts too small for k_rebin4).
+    const bool slab_single = overlap && ctx->tune.fuse_passes && ctx->tune.pipeline && K <= 64 && rebin_G == 4 && g.nx >= 3 &&
+                             g.ny >= 3;
+    auto slab_halo = [&](int buf, unsigned long long wait_seq, unsigned long long signal_seq) {
+        SlabHalo sh = no_slab_halo();
+        const size_t colp = (size_t)g.ny * g.K, colc = (size_t)g.ny;
+        const int ghost_col[2] = {g.ghost + g.ncol, 0};  // my first column lands in the LEFT neighbour's RIGHT ghost
+        sh.on = 1;
+        sh.myflag = reinterpret_cast<const unsigned long long *>(ctx->arena);
+        sh.wait_seq = wait_seq;
+        sh.signal_seq = signal_seq;
+        for (int side = 0; side < 2; ++side) {
+            char *pb = ctx->peer_base[side];
+            sh.hpos[side] = reinterpret_cast<double2 *>(pb + ctx->off_pos[buf]) + (size_t)ghost_col[side] * colp;
+            sh.hcnt[side] = reinterpret_cast<int *>(pb + ctx->off_cnt[buf]) + (size_t)ghost_col[side] * colc;
+            sh.hids[side] = ctx->use_ids ? reinterpret_cast<int *>(pb + ctx->off_ids[buf]) + (size_t)ghost_col[side] * colp
+                                         : nullptr;
+            sh.hflag[side] = reinterpret_cast<unsigned long long *>(pb) + (side == 0 ? 1 : 0);
+        }
+        sh.bcount = ctx->d_work + 7;
+        const long long last0 = (long long)(g.ncol - 1) * g.ny, end = (long long)g.ncol * g.ny;
+        sh.nbwarps = (g.ny + 7) / 8 + (int)((end + 7) / 8 - last0 / 8);
+        sh.err = ctx->d_err;
+        sh.spin_budget_ns = spin_budget_ns(ctx);
+        return sh;
+    };
+    SlabHalo order_wait = no_slab_halo();
     for (long long s = 0; s < nsweeps; ++s) {
         int order[4];
         double sx, sy;
         mc2d_schedule(ctx->prm.seed, ctx->sweep, g.dx, g.dy, plan->shift_grid, order, &sx, &sy);
-        if (sx != g.ox || sy != g.oy) {
+        order_wait.on = 0;
+        bool used_sb = !slab_single;  // the two-stream variants queue work on the boundary stream in every sweep
+        if ((sx != g.ox || sy != g.oy) && slab_single && fabs(sx - g.ox) > 1e-9 * g.dx && fabs(sy - g.oy) > 1e-9 * g.dy) {
+            Grid gn = g;
+            gn.ox = sx;
+            gn.oy = sy;
+            const int nb = 1 - ctx->cur;
+            const SlabHalo sh = slab_halo(nb, ctx->halo_seq, ctx->halo_seq + 1);
+            ++ctx->halo_seq;
+            CU(cudaMemsetAsync(ctx->d_work + 7, 0, sizeof(int), sa));
+            int rc = ktime_begin(ctx, 1);
+            if (rc) return rc;
+            k_rebin4<4, true><<<(ncell_owned + 63) / 64, 256, 0, sa>>>(
+                ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->use_ids ? ctx->ids[ctx->cur] : nullptr, ctx->pos[nb], ctx->cnt[nb],
+                ctx->use_ids ? ctx->ids[nb] : nullptr, gn, sx > g.ox ? 1 : -1, sy > g.oy ? 1 : -1, 0, ncell_owned, 0, 0,
+                ctx->d_err, sh);
+            ctx->launches++;
+            CU(cudaGetLastError());
+            if ((rc = ktime_end(ctx))) return rc;
+            ctx->cur = nb;
+            g = gn;
+            ctx->order_valid = false;
+            order_wait = sh;  // k_order_local waits for the neighbours' signal_seq
+        } else if (sx != g.ox || sy != g.oy) {
             Grid gn = g;
             gn.ox = sx;
             gn.oy = sy;
             const int nb = 1 - ctx->cur;
             if (overlap) {
+                used_sb = true;
                 int rc = join();
                 if (rc) return rc;
                 // the boundary columns read both ghosts of the old buffer: wait for the neighbours' last pushes
@@ -1811,10 +1873,10 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             }
         }
         if (persistent) {
-            if (overlap)  // the boundary stream may still be using the counters and the order of the last sweep
+            if (overlap && used_sb)  // the boundary stream may still be using the counters and the order of the last sweep
                 if (int rc = join()) return rc;
             if (!ctx->order_valid)
-                if (int rc = build_order(ctx)) return rc;
+                if (int rc = build_order(ctx, order_wait.on ? &order_wait : nullptr)) return rc;
             CU(cudaMemsetAsync(ctx->d_work, 0, 8 * sizeof(int), ctx->stream));
             // finished items per (colour pass, column pair) + 8 words of the slab pipeline (edge items per pass, frontier)
             CU(ctx->done_buf.ensure(sizeof(int) * (4 * (size_t)npairs + 8)));
@@ -1893,7 +1955,7 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             };
             int rc = MC2D_OK;
             if (fuse_halo) {
-                if ((rc = join())) return rc;  // the re-bin's boundary part and its push ran on the other stream
+                if (used_sb && (rc = join())) return rc;  // the re-bin's boundary part and its push ran on the other stream
                 const size_t colp = (size_t)g.ny * g.K, colc = (size_t)g.ny;
                 const int ghost_col[2] = {g.ghost + g.ncol, 0};  // my first column lands in the LEFT neighbour's RIGHT ghost
                 for (int side = 0; side < 2; ++side) {

@@ -39,11 +39,70 @@
 // of the j-th cell of that colour in that column pair, by falling (n_own, n_own + neighbours).
 // Stable counting sort: every rank depends only on the counts, never on timing.
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// Bounded waits.  Every in-kernel wait on a word that another rank (or another warp) writes has a time
+// budget (mc2d_tuning.spin_timeout_ms): a neighbour that failed before its launch, returned early or
+// died must not hang this GPU inside a cooperative kernel.  When the budget runs out the waiter sets
+// err[4]; every other wait sees that word and gives up at once, the kernel drains (on garbage), and
+// the host returns MC2D_ERR_PEER_TIMEOUT and drops the configuration.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mc2d_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// one look inside a spin loop: true when the wait must be abandoned (t0 = 0 on the first call)
+// (code, detail: which wait gave up first — err[6], err[7], reported with the failure)
+__device__ __forceinline__ bool spin_expired(int *err, unsigned long long budget_ns, unsigned long long &t0, int code = 0,
+                                             int detail = 0) {
+    if (*(volatile int *)&err[4]) return true;
+    const unsigned long long now = mc2d_globaltimer();
+    if (t0 == 0) t0 = now;
+    if (now - t0 > budget_ns) {
+        if (atomicExch(&err[4], 1) == 0) {
+            err[6] = code;
+            err[7] = detail;
+        }
+        return true;
+    }
+    return false;
+}
+__device__ __forceinline__ bool spin_until_ge(const unsigned long long *flag, unsigned long long want, int *err,
+                                              unsigned long long budget_ns, int code = 0) {
+    const volatile unsigned long long *f = flag;
+    unsigned long long t0 = 0;
+    while (*f < want) {
+        if (spin_expired(err, budget_ns, t0, code, (int)(want - *f))) return false;
+        __nanosleep(32);
+    }
+    return true;
+}
+
 __device__ __forceinline__ int warp_max_int(int v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(FULL_MASK, v, d));
     return v;
 }
+
+// Slab mode, halo inside the re-bin and work-order kernels (no second stream, no wait / push launches of their own):
+//  * k_rebin4: a warp that re-bins cells of the first or last owned column first waits until both neighbours have
+//    completed the ghost columns of the OLD buffer (flag words >= wait_seq), stores every particle it places also
+//    into the neighbour's ghost column of the NEW buffer, and the last such warp to finish signals signal_seq.
+//  * k_order_local: the CTAs of the slab-edge column pairs wait for that signal from the neighbour (they read the
+//    new ghost counts).
+struct SlabHalo {
+    int on;
+    const unsigned long long *myflag;  // [0] from left, [1] from right
+    unsigned long long wait_seq, signal_seq;
+    double2 *hpos[2];                  // [0] left neighbour's right-ghost column, [1] right neighbour's left-ghost column
+    int *hcnt[2];
+    int *hids[2];
+    unsigned long long *hflag[2];
+    int *bcount;                       // finished boundary warps of this launch
+    int nbwarps;                       // ... out of this many
+    int *err;
+    unsigned long long spin_budget_ns;
+};
 
 constexpr int ORDL_NB = 16;  // occupancy bins (15 and above share the first)
 constexpr int ORDL_MB = 8;   // candidate-count bins of width 8 (56 and above share the first)
@@ -54,11 +113,18 @@ constexpr int ORDL_WARPS = 4;
 // ol_smem: 3 columns x ny counts, then nay packed (bin << 16 | rank in warp); wc: NW x ORDL_BINS; bin_base: ORDL_BINS.
 template <int NW>
 __device__ __forceinline__ void order_local_task(const Grid &g, const int *cnt, int *perm, int p, int colour,
-                                                 int *ol_smem, int *wc, int *bin_base) {
+                                                 int *ol_smem, int *wc, int *bin_base, const SlabHalo &sh) {
     constexpr int NT = NW * 32;
     const int px = colour & 1, py = colour >> 1;
     const int nay = g.ny >> 1, npairs = g.ncol >> 1;
     const int lcx = g.ghost + 2 * p + px;
+    if (sh.on && ((p == 0 && px == 0) || (p == npairs - 1 && px == 1))) {  // reads a ghost column's counts
+        if (threadIdx.x == 0) {
+            spin_until_ge(sh.myflag + px, sh.signal_seq, sh.err, sh.spin_budget_ns, 5000 + px);
+            __threadfence();
+        }
+        __syncthreads();
+    }
     int *ol_cnt = ol_smem, *ol_key = ol_smem + 3 * g.ny;
     for (int c = 0; c < 3; ++c) {
         int col = lcx + c - 1;
@@ -140,11 +206,11 @@ __device__ __forceinline__ void order_local_task(const Grid &g, const int *cnt, 
 }
 
 // dynamic shared memory: 3 columns x ny counts, then nay keys
-__global__ void __launch_bounds__(ORDL_WARPS * 32) k_order_local(Grid g, const int *cnt, int *perm) {
+__global__ void __launch_bounds__(ORDL_WARPS * 32) k_order_local(Grid g, const int *cnt, int *perm, SlabHalo sh) {
     extern __shared__ int ol_smem[];
     __shared__ int wc[ORDL_WARPS * ORDL_BINS];
     __shared__ int bin_base[ORDL_BINS];
-    order_local_task<ORDL_WARPS>(g, cnt, perm, blockIdx.x, blockIdx.y, ol_smem, wc, bin_base);
+    order_local_task<ORDL_WARPS>(g, cnt, perm, blockIdx.x, blockIdx.y, ol_smem, wc, bin_base, sh);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -154,11 +220,11 @@ __global__ void __launch_bounds__(ORDL_WARPS * 32) k_order_local(Grid g, const i
 // k_rebin_g scans them (dx outer, dy inner, ascending): same slots.  A warp handles 32/G consecutive owned cells
 // starting at wl0 (all 32 lanes call this).
 // ------------------------------------------------------------------------------------------------
-template <int G>
+template <int G, bool HALO>
 __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, const int *__restrict__ cnt_o,
                                              const int *__restrict__ ids_o, double2 *pos_n, int *cnt_n, int *ids_n,
                                              const Grid &gn, int sx, int sy, int wl0, int w0, int n0, int w1, int n1,
-                                             int *err) {
+                                             int *err, const SlabHalo &sh) {
     const int lane = threadIdx.x & 31;
     const int gi = lane / G, sl = lane % G;
     const int wl = wl0 + gi;
@@ -168,6 +234,17 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
     const int gcx = gn.col0 + (lcx - gn.ghost);
     const int K = gn.K;
     const size_t obase = (size_t)(lcx * gn.ny + cy) * K;
+    // slab edge: 0 = first owned column (goes to the left neighbour), 1 = last owned column, -1 = interior
+    const int hs = (HALO && has) ? (lcx == gn.ghost ? 0 : (lcx == gn.ghost + gn.ncol - 1 ? 1 : -1)) : -1;
+    const bool bwarp = HALO && __any_sync(FULL_MASK, hs >= 0);
+    if (bwarp) {  // the old ghost columns must be complete before this warp reads them
+        if (lane == 0) {
+            spin_until_ge(sh.myflag + 0, sh.wait_seq, sh.err, sh.spin_budget_ns, 6000);
+            spin_until_ge(sh.myflag + 1, sh.wait_seq, sh.err, sh.spin_budget_ns, 6001);
+            __threadfence();
+        }
+        __syncwarp();
+    }
     int tc[4], ts[5];
     ts[0] = 0;
 #pragma unroll
@@ -179,7 +256,7 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
         }
         if (ocy < 0) ocy += gn.ny; else if (ocy >= gn.ny) ocy -= gn.ny;
         tc[c] = ocx * gn.ny + ocy;
-        ts[c + 1] = ts[c] + (has ? cnt_o[tc[c]] : 0);
+        ts[c + 1] = ts[c] + (has ? (bwarp ? __ldcg(&cnt_o[tc[c]]) : cnt_o[tc[c]]) : 0);
     }
     const int M = ts[4];
     const int KM = warp_max_int(M);
@@ -196,7 +273,7 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
             const int cc = q == 0 ? tc[0] : (q == 1 ? tc[1] : (q == 2 ? tc[2] : tc[3]));
             const int cs = q == 0 ? 0 : (q == 1 ? ts[1] : (q == 2 ? ts[2] : ts[3]));
             src = (size_t)cc * K + (k - cs);
-            p = pos_o[src];
+            p = bwarp ? __ldcg(&pos_o[src]) : pos_o[src];  // (a ghost cell: written by the neighbour, read past the L1)
             int ngx, ncy;
             sweep_cell_of(gn, p.x, p.y, ngx, ncy);
             take = (ngx == gcx && ncy == cy);
@@ -206,14 +283,38 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
             const int off = nout + __popc(m & lt);
             if (off < K) {
                 pos_n[obase + off] = p;
-                if (ids_n) ids_n[obase + off] = ids_o[src];
+                const int id = ids_n ? (bwarp ? __ldcg(&ids_o[src]) : ids_o[src]) : 0;
+                if (ids_n) ids_n[obase + off] = id;
+                if (hs >= 0) {  // ... and into the neighbour's ghost column of the new buffer
+                    // (no dynamic index into the kernel parameters: that would copy the struct to local memory)
+                    double2 *hp = hs == 0 ? sh.hpos[0] : sh.hpos[1];
+                    hp[(size_t)cy * K + off] = p;
+                    if (ids_n) {
+                        int *hi = hs == 0 ? sh.hids[0] : sh.hids[1];
+                        hi[(size_t)cy * K + off] = id;
+                    }
+                }
             }
         }
         nout += __popc(m);
     }
     if (has && sl == 0) {
         cnt_n[lcx * gn.ny + cy] = min(nout, K);
+        if (hs >= 0) {
+            int *hc = hs == 0 ? sh.hcnt[0] : sh.hcnt[1];
+            hc[cy] = min(nout, K);
+        }
         if (nout > K) atomicMax(&err[0], nout);
+    }
+    if (bwarp) {  // one more boundary warp done; the last one signals both neighbours
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0 && atomicAdd(sh.bcount, 1) == sh.nbwarps - 1) {
+            __threadfence_system();
+            *(volatile unsigned long long *)sh.hflag[0] = sh.signal_seq;
+            *(volatile unsigned long long *)sh.hflag[1] = sh.signal_seq;
+            __threadfence_system();
+        }
     }
 }
 
@@ -245,45 +346,6 @@ __device__ __forceinline__ double group_sum(double v) {
 #ifndef MC2D_SWEEPP_MIN_BLOCKS
 #define MC2D_SWEEPP_MIN_BLOCKS 3
 #endif
-
-// ------------------------------------------------------------------------------------------------
-// Bounded waits.  Every in-kernel wait on a word that another rank (or another warp) writes has a time
-// budget (mc2d_tuning.spin_timeout_ms): a neighbour that failed before its launch, returned early or
-// died must not hang this GPU inside a cooperative kernel.  When the budget runs out the waiter sets
-// err[4]; every other wait sees that word and gives up at once, the kernel drains (on garbage), and
-// the host returns MC2D_ERR_PEER_TIMEOUT and drops the configuration.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long mc2d_globaltimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// one look inside a spin loop: true when the wait must be abandoned (t0 = 0 on the first call)
-// (code, detail: which wait gave up first — err[6], err[7], reported with the failure)
-__device__ __forceinline__ bool spin_expired(int *err, unsigned long long budget_ns, unsigned long long &t0, int code = 0,
-                                             int detail = 0) {
-    if (*(volatile int *)&err[4]) return true;
-    const unsigned long long now = mc2d_globaltimer();
-    if (t0 == 0) t0 = now;
-    if (now - t0 > budget_ns) {
-        if (atomicExch(&err[4], 1) == 0) {
-            err[6] = code;
-            err[7] = detail;
-        }
-        return true;
-    }
-    return false;
-}
-__device__ __forceinline__ bool spin_until_ge(const unsigned long long *flag, unsigned long long want, int *err,
-                                              unsigned long long budget_ns, int code = 0) {
-    const volatile unsigned long long *f = flag;
-    unsigned long long t0 = 0;
-    while (*f < want) {
-        if (spin_expired(err, budget_ns, t0, code, (int)(want - *f))) return false;
-        __nanosleep(32);
-    }
-    return true;
-}
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);

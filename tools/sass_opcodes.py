@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "montecarlo_simulation_b200", "libmc2d.so")
 KERNELS = [("k_sweep_p<LJ, G=4>", "_Z9k_sweep_pILi0ELi4ELb0EEv9SweepArgsi", r"k_sweep_p<\(int\)0, \(int\)4, \(bool\)0>"),
            ("k_energy_p<LJ, G=4>", None, r"k_energy_p<\(int\)0, \(int\)4>"),
-           ("k_rebin4<4>", None, r"k_rebin4<\(int\)4>")]
+           ("k_rebin4<4>", None, r"k_rebin4<\(int\)4")]
 GROUPS = [("fp64 (DFMA DADD DMUL DSETP)", ("DFMA", "DADD", "DMUL", "DSETP")), ("MUFU", ("MUFU",)),
           ("integer / logic (IMAD IADD3 LOP3 SHF LEA ISETP SEL VIADD ...)",
            ("IMAD", "IADD3", "IADD", "LOP3", "SHF", "LEA", "ISETP", "SEL", "VIADD", "VIMNMX", "IDP", "PRMT", "I2F", "F2I",
@@ -100,7 +100,7 @@ def main():
     out = ["# SASS opcode mix of the hot kernels (sm_100a build of libmc2d.so)\n",
            "Static = instructions in the binary (`cuobjdump -sass`); dynamic = warp instructions executed in one launch "
            "(config #4, one colour pass / one reduction / one re-bin), from the source page of `%s`." % (os.path.basename(rep) if rep else "-")]
-    static_syms = {"k_sweep_p<LJ, G=4>": r"k_sweep_pILi0ELi4ELb0E", "k_energy_p<LJ, G=4>": r"k_energy_pILi0ELi4E", "k_rebin4<4>": r"k_rebin4ILi4E"}
+    static_syms = {"k_sweep_p<LJ, G=4>": r"k_sweep_pILi0ELi4ELb0E", "k_energy_p<LJ, G=4>": r"k_energy_pILi0ELi4E", "k_rebin4<4>": r"k_rebin4ILi4ELb0E"}
     for title, _, kre in KERNELS:
         out.append("\n## `%s`" % title)
         table(static_mix(static_syms[title]), "static", out)
