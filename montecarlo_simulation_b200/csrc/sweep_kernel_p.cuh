@@ -15,7 +15,7 @@
 //  * One launch does the four colour passes of a sweep.  Single rank: the items of all colours are ONE
 //    list (colour-major, then column pair, heavy-first inside a pair); an item of colour p+1 in
 //    column pair P waits — between items, never inside one — until the items of colour p in the
-//    pairs P-1, P, P+1 are finished (per-pair completion counters, ld.acquire.gpu).  No grid barrier:
+//    pairs P-1, P, P+1 are finished (per-pair completion counters).  No grid barrier:
 //    the tail of a colour overlaps the head of the next.  Slab / single-pass launches: items of one
 //    colour, heavy-first over all pairs, grid barrier between colours.
 //  * The index chain of an item (work ticket -> sorted cell -> 9 cell counts) is prefetched into
@@ -104,8 +104,11 @@ struct SlabHalo {
     unsigned long long spin_budget_ns;
 };
 
+#ifndef MC2D_ORDL_SHIFT
+#define MC2D_ORDL_SHIFT 3
+#endif
 constexpr int ORDL_NB = 16;  // occupancy bins (15 and above share the first)
-constexpr int ORDL_MB = 8;   // candidate-count bins of width 8 (56 and above share the first)
+constexpr int ORDL_MB = 64 >> MC2D_ORDL_SHIFT;  // candidate-count bins of width 2^MC2D_ORDL_SHIFT (the last ones share the first)
 constexpr int ORDL_BINS = ORDL_NB * ORDL_MB;
 constexpr int ORDL_WARPS = 4;
 
@@ -149,7 +152,7 @@ __device__ __forceinline__ void order_local_task(const Grid &g, const int *cnt, 
             const int n = ol_cnt[g.ny + cy];
             const int m = ol_cnt[ym] + ol_cnt[cy] + ol_cnt[yp] + ol_cnt[g.ny + ym] + ol_cnt[g.ny + yp] +
                           ol_cnt[2 * g.ny + ym] + ol_cnt[2 * g.ny + cy] + ol_cnt[2 * g.ny + yp] + n;
-            b = (ORDL_NB - 1 - min(n, ORDL_NB - 1)) * ORDL_MB + (ORDL_MB - 1 - min(m >> 3, ORDL_MB - 1));
+            b = (ORDL_NB - 1 - min(n, ORDL_NB - 1)) * ORDL_MB + (ORDL_MB - 1 - min(m >> MC2D_ORDL_SHIFT, ORDL_MB - 1));
         }
         const unsigned peers = __match_any_sync(FULL_MASK, b);
         const int r = __popc(peers & lt);
@@ -424,6 +427,18 @@ __device__ __forceinline__ double pair_scale() {
     return (POT == POT_LJ || POT == POT_WCA) ? 4.0 : 1.0;
 }
 
+// Everything another SM (or the neighbour GPU) may have written while this kernel runs — positions, counts, ids — is read
+// PAST THE L1 (cp.async.cg, ld.global.cg: the L2 is the point of coherence), and the completion counters that order those
+// reads are read with ld.relaxed.gpu: the data loads are issued only after the branch on the counter's value, so they
+// see at least what the writer had made visible (__threadfence) before it counted.  The alternative, ld.acquire.gpu
+// (= the same load + CCTL.IVALL, the SM's whole L1 dropped at every look) with L1-cached data loads, cost 49.2 against
+// 47.7 us per colour pass; -DMC2D_SWEEPP_IVALL builds it for A-B.
+#ifdef MC2D_SWEEPP_IVALL
+#define MC2D_LD_DONE "ld.acquire.gpu.global.s32"
+#else
+#define MC2D_LD_DONE "ld.relaxed.gpu.global.s32"
+#endif
+
 struct ItemMeta {
     int acy;              // row index of the cell inside its colour (from perm), -1: no cell
     int n_own;
@@ -553,6 +568,9 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         return (j < nay) ? pm[(size_t)p * nay + j] : -1;
     };
     auto load_counts = [&](int psv, int p, int acy, bool past_l1) {
+#ifndef MC2D_SWEEPP_IVALL
+        past_l1 = true;
+#endif
         ItemMeta m;
         m.acy = acy;
         m.n_own = 0;
@@ -561,7 +579,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
             const int c = colour_of(psv);
             int col3[3], row3[3];
             nbr_rows_cols(g, g.ghost + 2 * p + (c & 1), 2 * acy + (c >> 1), col3, row3);
-            m.n_own = a.cnt[col3[1] + row3[1]];
+            m.n_own = past_l1 ? __ldcg(&a.cnt[col3[1] + row3[1]]) : a.cnt[col3[1] + row3[1]];
             if (POT != POT_IDEAL) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -576,7 +594,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         return m;
     };
     // pipeline: an item of colour pass psv > 0 in column pair p reads cells that the previous colour pass wrote in the
-    // pairs p-1, p, p+1: wait until all their items are finished.  ld.acquire.gpu also drops this SM's L1 copies.
+    // pairs p-1, p, p+1: wait until all their items are finished (the cells are then read past the L1, see MC2D_LD_DONE).
     // block = false: one look (used while the current item is still open: it may itself be one of the items the next
     // one waits for, so blocking there would deadlock); block = true: spin (between items only).
     // Slab (pipeline + halo_fused): the column pairs do not wrap — beyond the slab edge lies the neighbour rank.  The item
@@ -600,9 +618,9 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
             bool ok = true, lok = true;
             if (psv > 0) {
                 int v0, v1, v2;
-                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v0) : "l"(d + pm) : "memory");
-                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v1) : "l"(d + p) : "memory");
-                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v2) : "l"(d + pp) : "memory");
+                asm volatile(MC2D_LD_DONE " %0, [%1];" : "=r"(v0) : "l"(d + pm) : "memory");
+                asm volatile(MC2D_LD_DONE " %0, [%1];" : "=r"(v1) : "l"(d + p) : "memory");
+                asm volatile(MC2D_LD_DONE " %0, [%1];" : "=r"(v2) : "l"(d + pp) : "memory");
                 ok = lok = min(v0, min(v1, v2)) >= ipp;
             }
             if (ok && edge) {
@@ -697,8 +715,13 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
             //      cp.async (no registers, all in flight together: one exposed memory latency per item) ----
             if (work) {
                 for (int s = sl; s < n_own; s += G) {
+#ifndef MC2D_SWEEPP_IVALL
+                    cp_async16_cg(&own[s], &a.pos[(size_t)cell * K + s]);
+                    if (a.ids) own_id[s] = __ldcg(&a.ids[(size_t)cell * K + s]);
+#else
                     cp_async16(&own[s], &a.pos[(size_t)cell * K + s]);
                     if (a.ids) own_id[s] = a.ids[(size_t)cell * K + s];
+#endif
                 }
                 // (own cells are written by this GPU only; the neighbours' cells of a boundary item include the ghost)
                 if (Ms > 0) {  // lane sl copies neighbour cells sl, sl + G, ...
@@ -715,10 +738,14 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
                         const int cb = oc == 0 ? col3[0] : (oc == 1 ? col3[1] : col3[2]);
                         const int rb = orow == 0 ? row3[0] : (orow == 1 ? row3[1] : row3[2]);
                         const double2 *src = a.pos + (size_t)(cb + rb) * K;
+#ifndef MC2D_SWEEPP_IVALL
+                        for (int s = 0; s < n; ++s) cp_async16_cg(&cand[pre + s], &src[s]);
+#else
                         if (bitem)
                             for (int s = 0; s < n; ++s) cp_async16_cg(&cand[pre + s], &src[s]);
                         else
                             for (int s = 0; s < n; ++s) cp_async16(&cand[pre + s], &src[s]);
+#endif
                     }
                 }
             }

@@ -425,7 +425,9 @@ def replay_trace(oracle, calc, Lx, Ly, xy0, trials, rcut):
 
 @pytest.mark.parametrize("name,ptype,kw,z", [("LennardJones", ol.LJ, dict(rcut=2.5), 0.05),
                                               ("WCA", ol.WCA, dict(rcut=2 ** (1 / 6)), 0.4),
-                                              ("AthermalStar", ol.ATHERMAL_STAR, dict(rcut=2.5, f=4.0, alpha=0.3), 0.05)])
+                                              ("AthermalStar", ol.ATHERMAL_STAR, dict(rcut=2.5, f=4.0, alpha=0.3), 0.05),
+                                              ("Yukawa", ol.YUKAWA, dict(rcut=2.5), 0.3),
+                                              ("ThermalStar", ol.THERMAL_STAR, dict(rcut=2.5, f=6.0, alpha=0.4, A0=1.5, kappa=1.1), 0.05)])
 def test_per_trial_dE_matches_oracle(mc, oracle, name, ptype, kw, z):
     """Every displacement / insertion / deletion dE the sweep kernel used in its acceptance rule,
     replayed on the oracle: 1e-10 relative."""
@@ -812,3 +814,104 @@ def test_pipelined_reupload_and_no_energy_option(mc):
         U1 = ctx.total_energy_virial(resync=True)[0]
         assert abs(st["energy"] - (U1 - U0)) < 1e-9 * max(1.0, abs(U0))  # sum of accepted dE since the upload
         assert ctx.stats()["energy"] == U1
+
+
+# ---- BASELINE configs at the stated gate ------------------------------------------------------------------
+
+def test_config1_nvt_lj_1024_matches_serial_reference(mc, oracle):
+    """Config #1: NVT LJ, N = 1024, L = 45.254834 (rho 0.5), rcut 2.5, T = 1, delta 0.1 (serial_src/main.cpp:102-144).
+    <E>/N and the pressure of the checkerboard sampler against the serial reference (oracle port, pinned bit for bit to
+    the reference), 6 independent serial chains with block-averaged standard errors.  The CI gate is 3 combined standard
+    errors (a 2-SE gate fails one honest run in twenty); the z-scores are printed, and the long run behind the
+    north-star's 2-SE statement is profiles/r02_stat_parity.md (tools/stat_parity.py: |z| = 0.7 and 0.2 there)."""
+    L, T, rcut, delta = 45.254834, 1.0, 2.5, 0.1
+    V = L * L
+    calc = oracle.calc(T, 0.0, ol.LJ, rcut)
+    start = lattice(32, 32, L, L, 0.2, 42)
+    e_s, p_s, se_e2, se_p2 = [], [], 0.0, 0.0
+    nchains = 6
+    for chain in range(nchains):
+        ser = oracle.mc(L, L, start, calc, rcut, delta, ol.NVT, 42 + chain)
+        ser.run(1500, 1500, 1)
+        ec, pc = [], []
+        for _ in range(300):
+            _, n1, e1 = ser.run(10, 10, 1)
+            ec.append(e1[-1] / 1024)
+            pc.append(oracle.pressure_celllist(calc, L, L, ser.particles()))
+        e_s.append(np.mean(ec))
+        p_s.append(np.mean(pc))
+        se_e2 += block_se(ec, 10) ** 2
+        se_p2 += block_se(pc, 10) ** 2
+    se_es, se_ps = math.sqrt(se_e2) / nchains, math.sqrt(se_p2) / nchains
+    with mc.Context(L, L, rcut, T=T, delta=delta, seed=42) as ctx:
+        ctx.upload(start)
+        ctx.run_sweeps(2000)
+        e_g, p_g = [], []
+        for _ in range(6000):
+            st = ctx.run_sweeps(5)
+            U, W, N = ctx.total_energy_virial()
+            assert N == 1024
+            e_g.append(U / N)
+            p_g.append(N / V * T + W / (2 * V))
+        assert relerr(st["energy"], U) < 1e-8
+    z_e = (np.mean(e_g) - np.mean(e_s)) / math.hypot(block_se(e_g), se_es)
+    z_p = (np.mean(p_g) - np.mean(p_s)) / math.hypot(block_se(p_g), se_ps)
+    print("config #1: <E>/N gpu %.5f serial %.5f z = %+.2f;  P gpu %.5f serial %.5f z = %+.2f"
+          % (np.mean(e_g), np.mean(e_s), z_e, np.mean(p_g), np.mean(p_s), z_p))
+    assert abs(z_e) < 3 and abs(z_p) < 3, (z_e, z_p)
+
+
+def test_wca_one_million_particles(mc, oracle):
+    """Config #4 with WCA (rcut = 2^(1/6), the reference's literal r^2 < 1.2599 test, potential.cpp:59-87): U and W of the
+    1 M-particle configuration against the oracle at 1e-10 — on the start AND after GCMC sweeps on cells widened to ~2.5
+    particles (cell_margin = -1) — bookkeeping exact, no refused insertion."""
+    n_side = 1000
+    L = n_side * math.sqrt(2.0)
+    rc = 2.0 ** (1.0 / 6.0)
+    xy = lattice(n_side, n_side, L, L, 0.2, 12345)
+    calc = oracle.calc(1.0, 0.0, ol.WCA, rc, 10.87)
+    with mc.Context(L, L, rc, potential="WCA", T=1.0, activity=10.87, delta=0.1, seed=7, cell_margin=-1.0) as ctx:
+        ctx.upload(xy)
+        info = ctx.info()
+        assert info.cell_dx >= 2 * rc * 0.99  # the cells were widened at the first upload
+        U0, W0, N0 = ctx.total_energy_virial()
+        assert N0 == len(xy)
+        assert relerr(U0, oracle.total_energy_celllist(calc, L, L, xy)) < REL
+        assert relerr(W0, oracle.total_virial_celllist(calc, L, L, xy)) < REL
+        st = ctx.run_sweeps(10, gc_per_cell=1)
+        assert st["overflow"] == 0 and st["attempted"][1] > 0 and st["accepted"][1] > 0
+        U1, W1, N1 = ctx.total_energy_virial()
+        assert N1 == st["n_particles"] and relerr(st["energy"], U1) < 1e-9
+        out = ctx.download()
+        assert len(out) == N1
+        assert relerr(U1, oracle.total_energy_celllist(calc, L, L, out)) < REL
+        assert relerr(W1, oracle.total_virial_celllist(calc, L, L, out)) < REL
+
+
+def test_refused_insertions_are_reported_per_call(mc):
+    """An insertion refused because its cell has no free slot biases the ensemble: mc2d_run_sweeps reports it with
+    MC2D_ERR_CELL_OVERFLOW for THAT call, with or without a statistics pointer; the sweeps have run, the counters are
+    valid, and a later call that refuses nothing succeeds again (the status is per call, stats.overflow the running total)."""
+    import ctypes as C
+
+    from montecarlo_simulation_b200 import api
+
+    L = 20.0
+    with mc.Context(L, L, 2.5, potential="Ideal", T=1.0, activity=3.0, delta=0.1, seed=3, cell_capacity=8) as ctx:
+        # <n> = z A = 18.75 per cell: the 8 slots fill up within a few sweeps.  Frozen grid: with the per-sweep shift a
+        # re-bin would need more than 8 slots in some new cell first, which is the other, fatal kind of overflow.
+        ctx.upload(np.zeros((0, 2)))
+        with pytest.raises(mc.MC2DError) as e:
+            ctx.run_sweeps(40, gc_per_cell=1, shift_grid=False)
+        assert e.value.status == api.ERR_CELL_OVERFLOW
+        st = ctx.stats()
+        assert st["overflow"] > 0 and st["sweeps_done"] == 40 and st["n_particles"] <= 64 * 8
+        plan = api.SweepPlan(1, 1, 0, 0)
+        assert ctx.L.mc2d_run_sweeps(ctx.h, 5, C.byref(plan), None) == api.ERR_CELL_OVERFLOW  # no statistics asked: still reported
+        ctx.set_activity(1e-9)  # deletions always succeed now, insertions never: the cells drain
+        try:
+            ctx.run_sweeps(80, gc_per_cell=1, shift_grid=False)  # (its first sweeps can still draw an insertion on a full cell)
+        except mc.MC2DError as e2:
+            assert e2.status == api.ERR_CELL_OVERFLOW
+        st2 = ctx.run_sweeps(5, gc_per_cell=1, shift_grid=False)  # nothing refused in THIS call: success, although the running total is > 0
+        assert st2["overflow"] >= st["overflow"] > 0 and st2["sweeps_done"] == 130
