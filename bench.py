@@ -579,8 +579,9 @@ def main():
         ctx.upload(host[:n_host], initial_energy=False)
         h2d += 16 * n_host
         st_e = ctx.run_sweeps(S, **plan1)
-        Ue, We, Ne = ctx.total_energy_virial(resync=True, allreduce=world > 1)
-        n_host = ctx.download_into(host)  # device -> pinned host (the caller's particle vector)
+        # one sample point: energy/virial reduction (re-sync) + device -> pinned host (the caller's particle vector); the
+        # reduction runs while the positions are on the bus (mc2d_sample)
+        Ue, We, Ne, n_host = ctx.sample_into(host, resync=True, allreduce=world > 1)
         d2h += 16 * n_host + 24 + 80  # positions + {U, W, N} + the stats block
         moves_e2e += sum(st_e["attempted"])
     barrier()
@@ -588,8 +589,8 @@ def main():
     e2e = {"value": allsum(moves_e2e) / dt, "unit": "moves/s", "h2d_bytes_per_step": h2d // args.e2e_steps,
            "d2h_bytes_per_step": d2h // args.e2e_steps, "steps": args.e2e_steps,
            "ms_per_step": 1e3 * dt / args.e2e_steps, "slot_reallocations": ctx.info().slot_allocs - allocs0,
-           "what": "mc2d_upload_ex(host xy, NO_ENERGY) + %d sweeps + energy/virial (resync) + mc2d_download(host xy) per step; "
-                   "copies chunked and overlapped with the binning / compaction kernels" % S}
+           "what": "mc2d_upload_ex(host xy, NO_ENERGY) + %d sweeps + mc2d_sample (energy/virial with re-sync + download to host xy) "
+                   "per step; copies chunked and overlapped with the binning / compaction / reduction kernels" % S}
     halo_mode = ctx.info().halo_mode
     grid_now = [info.nx, info.ny]
     cellcap = info.cell_capacity

@@ -142,6 +142,11 @@ int mc2d_upload_ex(mc2d_ctx *ctx, const double *xy, const int *ids, long long n,
  * carry id -1. */
 int mc2d_download(mc2d_ctx *ctx, double *xy, int *ids, long long cap, long long *n_out);
 int mc2d_num_particles(mc2d_ctx *ctx, long long *n_local);
+/* One sample point (MonteCarlo::recordObservables: Logging::logSimulationData + logPositions, MC.cpp:62-78): the
+ * energy/virial reduction of mc2d_total_energy_virial AND the download of mc2d_download in one call — the reduction runs
+ * on the device while the positions are still on their way to the host. */
+int mc2d_sample(mc2d_ctx *ctx, int resync, int allreduce, double *U, double *W, long long *N, double *xy, int *ids,
+                long long cap, long long *n_out);
 
 /* -- the step loop (MonteCarlo::run, MC.cpp:31-78; MonteCarloNVT_MPI::run, MC_parallel.cpp:57-114) */
 int mc2d_run_sweeps(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_plan *plan, mc2d_stats *stats_out);

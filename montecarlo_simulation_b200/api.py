@@ -92,7 +92,7 @@ EXPORTS = [
     "mc2d_comm_unique_id", "mc2d_comm_init", "mc2d_allreduce_stats", "mc2d_get_info", "mc2d_get_stream",
     "mc2d_synchronize", "mc2d_set_kernel_timing", "mc2d_calc_neighbor_list", "mc2d_calc_energy_virial_bruteforce",
     "mc2d_rescale_try", "mc2d_rescale_finish", "mc2d_probe_point", "mc2d_probe_particle", "mc2d_apply_probe", "mc2d_measure_fp64_peak",
-    "mc2d_get_tuning", "mc2d_set_tuning", "mc2d_upload_ex",
+    "mc2d_get_tuning", "mc2d_set_tuning", "mc2d_upload_ex", "mc2d_sample",
 ]
 
 _lib = None
@@ -122,6 +122,7 @@ def load_library() -> C.CDLL:
     L.mc2d_sweep_schedule.argtypes = [C.c_uint64, C.c_uint64, d, d, i, ip, dp, dp]
     L.mc2d_upload.argtypes = [vp, vp, vp, ll]
     L.mc2d_upload_ex.argtypes = [vp, vp, vp, ll, C.c_uint]
+    L.mc2d_sample.argtypes = [vp, i, i, dp, dp, C.POINTER(ll), vp, vp, ll, C.POINTER(ll)]
     L.mc2d_download.argtypes = [vp, vp, vp, ll, C.POINTER(ll)]
     L.mc2d_num_particles.argtypes = [vp, C.POINTER(ll)]
     L.mc2d_run_sweeps.argtypes = [vp, ll, C.POINTER(SweepPlan), C.POINTER(Stats)]
@@ -320,6 +321,14 @@ class Context:
         m = C.c_longlong()
         self._check(self.L.mc2d_download(self.h, xy.ctypes.data, None, xy.shape[0], C.byref(m)))
         return m.value
+
+    def sample_into(self, xy: np.ndarray, resync=True, allreduce=False):
+        """mc2d_sample: energy/virial reduction + download into a caller-owned (cap, 2) float64 array -> (U, W, N, count)"""
+        assert xy.dtype == np.float64 and xy.flags["C_CONTIGUOUS"] and xy.ndim == 2 and xy.shape[1] == 2
+        U, W, N, m = C.c_double(), C.c_double(), C.c_longlong(), C.c_longlong()
+        self._check(self.L.mc2d_sample(self.h, int(resync), int(allreduce), C.byref(U), C.byref(W), C.byref(N), xy.ctypes.data,
+                                       None, xy.shape[0], C.byref(m)))
+        return U.value, W.value, N.value, m.value
 
     def download(self, with_ids=False):
         n = self.num_particles()

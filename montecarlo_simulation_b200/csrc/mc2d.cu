@@ -1025,8 +1025,9 @@ extern "C" int mc2d_num_particles(mc2d_ctx *ctx, long long *n_local) {
     return count_particles(ctx, n_local);
 }
 
-extern "C" int mc2d_download(mc2d_ctx *ctx, double *xy, int *ids, long long cap, long long *n_out) {
-    if (!ctx || !n_out) return MC2D_ERR_INVALID;
+// download, optionally with the energy/virial reduction running behind the device -> host copies (mc2d_sample)
+static int download_impl(mc2d_ctx *ctx, double *xy, int *ids, long long cap, long long *n_out, bool with_energy, bool resync,
+                         bool allreduce, double *U, double *W, long long *N) {
     if (!ctx->have_particles) FAIL(MC2D_ERR_STATE, "no particles uploaded");
     CU(cudaSetDevice(ctx->dev));
     const Grid &g = ctx->g;
@@ -1048,7 +1049,10 @@ extern "C" int mc2d_download(mc2d_ctx *ctx, double *xy, int *ids, long long cap,
     ctx->n_last = n;
     *n_out = n;
     if (n > cap) FAIL(MC2D_ERR_INVALID, "download needs room for %lld particles, caller gave %lld", n, cap);
-    if (n == 0) return MC2D_OK;
+    if (n == 0) {
+        if (with_energy) return energy_on_slots(ctx, U, W, N, resync, allreduce);
+        return MC2D_OK;
+    }
     CU(ctx->spos.ensure(sizeof(double2) * (size_t)n));
     CU(ctx->sids.ensure(sizeof(int) * (size_t)n));
     for (int c = 0; c < nch; ++c) {
@@ -1069,9 +1073,30 @@ extern "C" int mc2d_download(mc2d_ctx *ctx, double *xy, int *ids, long long cap,
         if (xy) CU(cudaMemcpyAsync(xy + 2 * o0, ctx->spos.as<double2>() + o0, sizeof(double2) * (size_t)(o1 - o0), cudaMemcpyDeviceToHost, cs));
         if (ids) CU(cudaMemcpyAsync(ids + o0, ctx->sids.as<int>() + o0, sizeof(int) * (size_t)(o1 - o0), cudaMemcpyDeviceToHost, cs));
     }
+    // (mc2d_sample: the reduction runs on the main stream while the copies are still on the bus)
+    if (with_energy)
+        if ((rc = energy_on_slots(ctx, U, W, N, resync, allreduce))) return rc;
     if (nch > 1) CU(cudaStreamSynchronize(ctx->stream_b));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
+    return MC2D_OK;
+}
+
+extern "C" int mc2d_download(mc2d_ctx *ctx, double *xy, int *ids, long long cap, long long *n_out) {
+    if (!ctx || !n_out) return MC2D_ERR_INVALID;
+    return download_impl(ctx, xy, ids, cap, n_out, false, false, false, nullptr, nullptr, nullptr);
+}
+
+extern "C" int mc2d_sample(mc2d_ctx *ctx, int resync, int allreduce, double *U, double *W, long long *N, double *xy, int *ids,
+                           long long cap, long long *n_out) {
+    if (!ctx || !n_out) return MC2D_ERR_INVALID;
+    double u = 0, w = 0;
+    long long n = 0;
+    const int rc = download_impl(ctx, xy, ids, cap, n_out, true, resync != 0, allreduce != 0, &u, &w, &n);
+    if (rc) return rc;
+    if (U) *U = u;
+    if (W) *W = w;
+    if (N) *N = n;
     return MC2D_OK;
 }
 

@@ -814,6 +814,11 @@ def test_pipelined_reupload_and_no_energy_option(mc):
         U1 = ctx.total_energy_virial(resync=True)[0]
         assert abs(st["energy"] - (U1 - U0)) < 1e-9 * max(1.0, abs(U0))  # sum of accepted dE since the upload
         assert ctx.stats()["energy"] == U1
+        # mc2d_sample = reduction + download in one call (the reduction overlaps the copies): the same numbers
+        buf = np.empty((len(xy) + 4096, 2))
+        Us, Ws, Ns, m = ctx.sample_into(buf, resync=False)
+        ref = ctx.download()
+        assert (Us, Ws, Ns) == ctx.total_energy_virial() and m == Ns == len(ref) and (buf[:m] == ref).all()
 
 
 # ---- BASELINE configs at the stated gate ------------------------------------------------------------------
