@@ -326,21 +326,35 @@ __global__ void __launch_bounds__(256) k_energy_p(const double2 *pos, const int 
     }
     cp_async_wait_all();
     __syncwarp();
-    for (int k = sl; k < ntot; k += G) cand[k] = to_local(cand[k], x_lo, y_lo, g, hLx, hLy);
+    // to cell-local coordinates, in place; only a cell on the rim of the periodic box (or of the shifted grid) can see a
+    // periodic image, everywhere else the conversion is two exact subtractions (as in k_sweep_p)
+    const unsigned cand_s = (unsigned)__cvta_generic_to_shared(cand);
+    const unsigned cand_e = cand_s + 16u * (unsigned)ntot, nb_e = cand_s + 16u * (unsigned)(work ? Mf : 0);
+    {
+        const bool rim = work && (gcx == 0 || gcx >= g.nx - 2 || cy == 0 || cy >= g.ny - 2);
+        if (__any_sync(FULL_MASK, rim)) {
+            for (unsigned q = cand_s + 16u * sl; q < cand_e; q += 16u * G) sts_d2(q, to_local(lds_d2(q), x_lo, y_lo, g, hLx, hLy));
+        } else {
+            for (unsigned q = cand_s + 16u * sl; q < cand_e; q += 16u * G) {
+                const double2 v = lds_d2(q);
+                sts_d2(q, make_double2(v.x - x_lo, v.y - y_lo));
+            }
+        }
+    }
     __syncwarp();
 
     // Per-group loop bounds: the groups of a warp diverge on the trip counts only (equally full cells share a warp,
-    // k_order_local), there is no shuffle inside the loops.
+    // k_order_local), there is no shuffle inside the loops.  Shared-window addresses, one address register per loop.
     double a = 0.0, b = 0.0, accU = 0.0, accW = 0.0;
     unsigned int evals = 0;
     for (int i = 0; i < (work ? n_own : 0); ++i) {
-        const double2 ui = cand[Mf + i];
-        const int first_own = Mf + i;  // own candidates count from j > i
-        for (int k = sl; k < ntot; k += G) {
-            const double2 c = cand[k];
+        const unsigned self_s = nb_e + 16u * (unsigned)i;  // own candidates count from j > i
+        const double2 ui = lds_d2(self_s);
+        for (unsigned q = cand_s + 16u * sl; q < cand_e; q += 16u * G) {
+            const double2 c = lds_d2(q);
             const double dx = c.x - ui.x, dy = c.y - ui.y;
             const double r2 = fma(dx, dx, dy * dy);
-            bool ok = (k < Mf || k > first_own) && r2 <= r2cut;  // inclusive cutoff, cell_list.cpp:62
+            bool ok = (q < nb_e || q > self_s) && r2 <= r2cut;  // inclusive cutoff, cell_list.cpp:62
             if (POT == POT_LJ || POT == POT_WCA) {
                 if (POT == POT_WCA) ok = ok && r2 < 1.2599;
                 const double r2m = __hiloint2double(ok ? __double2hiint(r2) : 0x7E37E43C, __double2loint(r2));

@@ -279,16 +279,21 @@ double ref_time_moves(void *h, size_t nSweeps, size_t fUpdateCell, int gcmc, lon
     *moves = done;
     return std::chrono::duration<double>(b - a).count();
 }
-// The reference's sampler without its stale-cell-list shortcut: per sweep N x stepBruteForce (MC.cpp: exact dE over
-// all particles), then — for GCMC — a cell rebuild, one grandCanonicalMove and another rebuild, so that the insertion /
-// deletion energy is evaluated on a list that knows every particle.  Same moves, same acceptance rules, same RNG as
-// MonteCarlo::run; only the neighbour search is exact.  Used by tools/stat_parity.py for hard-core potentials, where the
-// stale list of the stock loop lets overlaps through.  Returns the particle count; *energy = running energy.
+// The reference's sampler without its stale-cell-list shortcut: the cell list is rebuilt before EVERY trial (N x
+// [updateCellList + stepCellList], then — for GCMC — a rebuild, one grandCanonicalMove and another rebuild), so that
+// every dE is evaluated on a list that knows every particle in its current cell.  Same moves, same acceptance rules,
+// same RNG stream as MonteCarlo::run; only the neighbour search is exact (O(N) per trial: small systems only; the
+// reference's own stepBruteForce recomputes the TOTAL energy twice per trial, O(N^2), and is no alternative).  Used by
+// tools/stat_parity.py where the stale list of the stock loop lets overlaps through (hard cores).
+// Returns the particle count; *energy = running energy.
 int ref_mc_run_exact(void *h, size_t nSweeps, int gcmc, double *energy) {
     RefMC *m = static_cast<RefMC *>(h);
     for (size_t s = 0; s < nSweeps; ++s) {
         const size_t N = m->particles.size();
-        for (size_t i = 0; i < N; ++i) m->mc->stepBruteForce();
+        for (size_t i = 0; i < N; ++i) {
+            m->mc->updateCellList();
+            m->mc->stepCellList();
+        }
         if (gcmc) {
             m->mc->updateCellList();
             m->mc->grandCanonicalMove();

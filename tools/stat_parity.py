@@ -13,8 +13,8 @@ How the reference is driven (ref_mode):
   run    MonteCarlo::run with a cell rebuild EVERY sweep (fUpdateCell = 1): the stock loop at its most exact.  Between
          rebuilds the reference evaluates dE on a stale list: a particle that crossed a cell wall, or one
          a GC move has just inserted, can be missed.  Harmless for soft tails, not for hard cores.
-  exact  the same moves (stepBruteForce = exact dE over all particles, grandCanonicalMove on a freshly rebuilt list;
-         oracle/ref_shim.cpp: ref_mc_run_exact).  Used where `run` lets overlaps through (WCA) and for the small cases.
+  exact  the same moves with the cell list rebuilt before EVERY trial (oracle/ref_shim.cpp: ref_mc_run_exact; O(N) per
+         trial).  Used where `run` lets overlaps through (WCA) and for the small cases.
 Dense states start the reference chains from decorrelated snapshots of the equilibrated GPU chain: the serial sampler
 makes ONE insertion/deletion trial per sweep of N displacements (MC.cpp:45-52), so condensing a liquid from the gas
 takes it millions of sweeps; where it starts does not change what it samples.
