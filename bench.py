@@ -553,7 +553,7 @@ def main():
 
     # DRAM bytes per launch of the sweep kernel from the newest committed `ncu --set full` capture
     import glob
-    trs = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")), key=os.path.getmtime)
+    trs = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")))  # rNNx names sort by round and capture
     if trs:
         try:
             roofline["traffic"] = json.load(open(trs[-1])).get("k_sweep_dram_bytes_per_launch")
