@@ -13,7 +13,9 @@ variants = sys.argv[1:] or [""]
 sweeps = int(os.environ.get("AB_SWEEPS", "20"))
 npart = int(os.environ.get("AB_PARTICLES", "1000000"))
 wl = bench.workload(1, 0, npart)
-with m.Context(wl["L"], wl["L"], bench.RCUT, T=bench.T_BENCH, activity=bench.Z_LJ_T1_RHO05, delta=bench.DELTA, seed=42) as ctx:
+base = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in os.environ.get("AB_BASE_TUNING", "").split()}  # for variant libraries
+with m.Context(wl["L"], wl["L"], bench.RCUT, T=bench.T_BENCH, activity=bench.Z_LJ_T1_RHO05, delta=bench.DELTA, seed=42,
+               tuning=base) as ctx:
     ctx.upload(wl["xy"])
     ctx.run_sweeps(200, disp_per_particle=1, gc_per_cell=1)
     start = ctx.download()
