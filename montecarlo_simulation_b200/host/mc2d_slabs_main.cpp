@@ -11,7 +11,9 @@
 //   <basename>.thermo.csv  header "timestep,N_global,rho,T,U,W,P,V", 17 significant digits
 //                          (logging_data_mpi.cpp:56-67)
 //   <basename>.dump        LAMMPS dump frames "id type x y z", type = rank + 1
-//                          (logging_traj_mpi.cpp:268-303, Mode::MPIIO with rank_as_type)
+//                          (logging_traj_mpi.cpp:268-303, Mode::MPIIO with rank_as_type — what mpi_src/main.cpp:164
+//                          asks for; written by LoggingTrajSlabs, slab_traj_logger.hpp).  The optional key
+//                          `traj_mode perrank | gather | shared` selects the class's other file modes.
 // Differences: ensemble GCMC is accepted (mu is the activity, as in serial_src; the reference's MPI
 // driver is NVT only); `init lattice` starts from a jittered square lattice instead of uniformly
 // random points (which overlap and give LJ energies of 1e30); rcut is never shrunk silently.
@@ -34,54 +36,14 @@
 
 #include "mc2d.h"
 #include "mc2d_host.hpp"
+#include "slab_ranks.hpp"
+#include "slab_traj_logger.hpp"
 
 namespace {
 
-// one page shared by the ranks
-struct Shared {
-    std::atomic<int> arrived;
-    std::atomic<int> generation;
-    std::atomic<int> turn;
-    std::atomic<int> failed;
-    unsigned char bcast_buf[256];
-    long long counts[64];
-};
-
-struct Ranks {
-    Shared *sh;
-    int rank, size;
-    void barrier() const {
-        const int gen = sh->generation.load();
-        if (sh->arrived.fetch_add(1) + 1 == size) {
-            sh->arrived.store(0);
-            sh->generation.fetch_add(1);
-        } else {
-            while (sh->generation.load() == gen) {
-                if (sh->failed.load()) throw std::runtime_error("another rank failed");
-                usleep(50);
-            }
-        }
-    }
-    void bcast(void *buf, std::size_t bytes, int root) const {
-        if (bytes > sizeof sh->bcast_buf) throw std::runtime_error("bcast buffer too small");
-        if (rank == root) std::memcpy(sh->bcast_buf, buf, bytes);
-        barrier();
-        if (rank != root) std::memcpy(buf, sh->bcast_buf, bytes);
-        barrier();
-    }
-    // ranks run f one after the other in rank order (append to one file)
-    template <class F>
-    void in_turn(F &&f) const {
-        barrier();
-        while (sh->turn.load() != rank) {
-            if (sh->failed.load()) throw std::runtime_error("another rank failed");
-            usleep(50);
-        }
-        f();
-        sh->turn.store(rank + 1 == size ? 0 : rank + 1);
-        barrier();
-    }
-};
+using mc2d_slabs::LoggingTrajSlabs;
+using mc2d_slabs::Ranks;
+using mc2d_slabs::Shared;
 
 double get_or(Input &in, const std::string &key, double dflt) {
     try {
@@ -160,9 +122,15 @@ int run_rank(const Ranks &R, const std::string &input_file) {
         csv.open(basename + ".thermo.csv", std::ios::out | std::ios::trunc);
         if (!csv) throw std::runtime_error("cannot open " + basename + ".thermo.csv");
         csv << "timestep,N_global,rho,T,U,W,P,V\n";
-        std::ofstream(basename + ".dump", std::ios::out | std::ios::trunc);  // truncate
     }
     R.barrier();
+    const std::string traj_mode = input.getFilename("traj_mode");
+    if (!traj_mode.empty() && traj_mode != "perrank" && traj_mode != "gather" && traj_mode != "shared")
+        throw std::invalid_argument("traj_mode must be perrank, gather or shared, got '" + traj_mode + "'");
+    LoggingTrajSlabs traj(basename,
+                          traj_mode == "perrank" ? LoggingTrajSlabs::Mode::PerRank
+                                                 : (traj_mode == "gather" ? LoggingTrajSlabs::Mode::GatherRoot : LoggingTrajSlabs::Mode::MPIIO),
+                          R, /*append=*/false, /*rank_as_type=*/true);
 
     int timestep = 0;
     auto log_frame = [&]() {
@@ -175,22 +143,9 @@ int run_rank(const Ranks &R, const std::string &input_file) {
                 << U << "," << W << "," << P << "," << V << "\n";
             csv.flush();
         }
-        // dump frame (logging_traj_mpi.cpp:268-303): header by rank 0, bodies in rank order, global 1-based ids
+        // dump frame (MC_parallel.cpp:102)
         mc.download(owned);
-        R.sh->counts[R.rank] = (long long)owned.size();
-        R.barrier();
-        long long id_base = 0;
-        for (int r = 0; r < R.rank; ++r) id_base += R.sh->counts[r];
-        R.in_turn([&]() {
-            std::ofstream d(basename + ".dump", std::ios::out | std::ios::app);
-            if (R.rank == 0)
-                d << "ITEM: TIMESTEP\n" << timestep << "\nITEM: NUMBER OF ATOMS\n" << Ng << "\nITEM: BOX BOUNDS pp pp ff\n"
-                  << 0.0 << " " << Lx << "\n" << 0.0 << " " << Ly << "\n" << 0.0 << " " << 0.0
-                  << "\nITEM: ATOMS id type x y z\n";
-            d << std::setprecision(17);
-            for (std::size_t i = 0; i < owned.size(); ++i)
-                d << id_base + 1 + (long long)i << " " << R.rank + 1 << " " << owned[i].x << " " << owned[i].y << " 0\n";
-        });
+        traj.log_dump(owned, box, timestep);
     };
     auto run_phase = [&](std::size_t nsweeps, const char *label) {
         if (nsweeps == 0) return;
@@ -255,6 +210,7 @@ int main(int argc, char *argv[]) {
     sh->generation = 0;
     sh->turn = 0;
     sh->failed = 0;
+    sh->session = (long long)getpid();
     std::vector<pid_t> kids;
     for (int r = 0; r < size; ++r) {
         const pid_t c = fork();

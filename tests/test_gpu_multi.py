@@ -87,3 +87,63 @@ os._exit(0)
     sys.stdout.write(res.stdout[-2000:])
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
     assert "status 9" in res.stdout
+
+
+def _dump_frames(path):
+    """LAMMPS dump -> list of (timestep, natoms, sorted [(x, y)] as written, [types])."""
+    lines = open(path).read().splitlines()
+    frames, i = [], 0
+    while i < len(lines):
+        assert lines[i] == "ITEM: TIMESTEP"
+        ts, n = int(lines[i + 1]), int(lines[i + 3])
+        assert lines[i + 8] == "ITEM: ATOMS id type x y z"
+        rows = [l.split() for l in lines[i + 9:i + 9 + n]]
+        assert [int(r[0]) for r in rows] == list(range(1, n + 1))
+        frames.append((ts, n, sorted((r[2], r[3]) for r in rows), [int(r[1]) for r in rows]))
+        i += 9 + n
+    return frames
+
+
+@pytest.mark.parametrize("ensemble", ["NVT", "GCMC"])
+def test_slab_driver_two_ranks_equals_one_rank(tmp_path, ensemble):
+    """mc2d_slabs (= mpi_src/main.cpp:28-204 + MC_parallel.cpp:57-114 on GPU slabs) with 2 forked ranks writes the same
+    thermo rows (logging_data_mpi.cpp:56-67) and — as a set, at 17 digits — the same particles into the dump
+    (logging_traj_mpi.cpp:268-303) as with 1 rank; types are rank + 1; the gather-to-root file mode of the trajectory
+    logger gives the same frames at 6 digits."""
+    if _ndev() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    host = os.path.join(ROOT, "montecarlo_simulation_b200", "host")
+    subprocess.check_call(["make", "-s", "-C", host, "all"])
+
+    def drive(tag, nranks, extra=()):
+        base = tmp_path / tag
+        inp = tmp_path / (tag + ".txt")
+        inp.write_text("\n".join([
+            "Lx 120.0", "Ly 50.0", "N 3000", "rcut 2.5", "T 1.0", "nSteps 30", "eSteps 10", "outputFreq 10",
+            "cellUpdateFreq 10", "delta 0.1", "seed 7", "potential LennardJones", "ensemble " + ensemble, "mu 0.3",
+            "init lattice", "out_xyz %s.xyz" % base, "out_data %s.csv" % base, *extra, ""]))
+        out = subprocess.run([os.path.join(host, "mc2d_slabs"), str(inp), str(nranks)], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        return base
+
+    one, two = drive("one", 1), drive("two", 2)
+    rows1 = open(str(one) + ".thermo.csv").read().splitlines()
+    rows2 = open(str(two) + ".thermo.csv").read().splitlines()
+    assert rows1[0] == rows2[0] == "timestep,N_global,rho,T,U,W,P,V" and len(rows1) == len(rows2) == 5
+    for a, b in zip(rows1[1:], rows2[1:]):
+        fa, fb = [float(v) for v in a.split(",")], [float(v) for v in b.split(",")]
+        assert fa[:4] == fb[:4] and fa[7] == fb[7]  # timestep, N, rho, T, V
+        for k in (4, 5, 6):  # U, W, P: summation order only
+            assert abs(fa[k] - fb[k]) <= 1e-11 * max(1.0, abs(fa[k]))
+    f1, f2 = _dump_frames(str(one) + ".dump"), _dump_frames(str(two) + ".dump")
+    assert len(f1) == len(f2) == 4
+    for (ts1, n1, xy1, t1), (ts2, n2, xy2, t2) in zip(f1, f2):
+        assert ts1 == ts2 and n1 == n2 and xy1 == xy2
+        assert set(t1) == {1} and set(t2) == {1, 2} and t2 == sorted(t2)
+    if ensemble == "GCMC":
+        assert len({f[1] for f in f1}) > 1  # the particle number moved
+    gat = drive("gat", 2, ["traj_mode gather"])
+    fg = _dump_frames(str(gat) + ".dump")
+    assert [(f[0], f[1], f[3]) for f in fg] == [(f[0], f[1], f[3]) for f in f2]
+    per = drive("per", 2, ["traj_mode perrank"])
+    assert os.path.exists(str(per) + ".rank0000.dump") and os.path.exists(str(per) + ".rank0001.dump")
