@@ -1177,7 +1177,7 @@ static int build_order(mc2d_ctx *ctx, const SlabHalo *wait = nullptr) {
 
 // K4 on the slot layout through the sorted items (k_energy_p).  *done = false: not applicable here (tiny grid,
 // huge cells) or an item did not fit its shared memory — the caller uses k_energy_virial_g instead.
-static int launch_energy_items(mc2d_ctx *ctx, double *U, double *W, bool *done) {
+static int launch_energy_items(mc2d_ctx *ctx, double *U, double *W, bool *done, bool resync) {
     *done = false;
     const Grid &g = ctx->g;
     if (g.nx < 4 || g.ny < 4) return MC2D_OK;
@@ -1200,12 +1200,20 @@ static int launch_energy_items(mc2d_ctx *ctx, double *U, double *W, bool *done) 
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     DISPATCH_POT(ctx->prm.potential, {
         if (G == 4) {
-            CU(cudaFuncSetAttribute(k_energy_p<POT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            LaunchShape &ls = ctx->launch_shapes[(const void *)k_energy_p<POT, 4>];
+            if (!ls.occ) {
+                CU(cudaFuncSetAttribute(k_energy_p<POT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                ls.occ = 1;
+            }
             k_energy_p<POT, 4><<<nblocks, wpb * 32, smem, ctx->stream>>>(
                 ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->order_buf.as<int>(), g, ctx->pp, ctx->r2cut, nitems, cap,
                 (int)lay.per_group, pU, pW, ctx->d_pair_stats, ctx->d_err);
         } else {
-            CU(cudaFuncSetAttribute(k_energy_p<POT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            LaunchShape &ls = ctx->launch_shapes[(const void *)k_energy_p<POT, 8>];
+            if (!ls.occ) {
+                CU(cudaFuncSetAttribute(k_energy_p<POT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                ls.occ = 1;
+            }
             k_energy_p<POT, 8><<<nblocks, wpb * 32, smem, ctx->stream>>>(
                 ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->order_buf.as<int>(), g, ctx->pp, ctx->r2cut, nitems, cap,
                 (int)lay.per_group, pU, pW, ctx->d_pair_stats, ctx->d_err);
@@ -1218,9 +1226,18 @@ static int launch_energy_items(mc2d_ctx *ctx, double *U, double *W, bool *done) 
     CU(cudaMemcpyAsync(hp->uw, ctx->d_energy + 1, sizeof hp->uw, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(hp->ps, ctx->d_pair_stats, sizeof hp->ps, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(&hp->ovf, ctx->d_err + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    // the running energy takes the recomputed value before the one synchronisation of this call; should an item have
+    // overflowed its shared memory (never seen), the running energy is restored and the caller's fallback redoes it
+    if (resync) {
+        CU(cudaMemcpyAsync(ctx->d_energy + 3, ctx->d_energy, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_energy, ctx->d_energy + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
-    if (hp->ovf) return MC2D_OK;
+    if (hp->ovf) {
+        if (resync) CU(cudaMemcpyAsync(ctx->d_energy, ctx->d_energy + 3, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        return MC2D_OK;
+    }
     const double *uw = hp->uw;
     const unsigned long long *ps = hp->ps;
     float ms = 0;
@@ -1285,13 +1302,19 @@ static int energy_on_slots(mc2d_ctx *ctx, double *U, double *W, long long *N, bo
     int rc = MC2D_OK;
     // the particle count rides on the synchronisation of the energy launch
     if ((rc = count_particles_async(ctx))) return rc;
-    if (!ctx->tune.energy_unstaged) rc = launch_energy_items(ctx, U, W, &done);
+    if (!ctx->tune.energy_unstaged) rc = launch_energy_items(ctx, U, W, &done, resync);
     if (rc) return rc;
-    if (!done) rc = launch_energy(ctx, v, g.ncol * g.ny, half, false, nullptr, nullptr, U, W);
-    if (rc) return rc;
+    bool pending = false;  // work on the stream behind the last synchronisation
+    if (!done) {
+        rc = launch_energy(ctx, v, g.ncol * g.ny, half, false, nullptr, nullptr, U, W);
+        if (rc) return rc;
+        if (resync) {
+            CU(cudaMemcpyAsync(ctx->d_energy, ctx->d_energy + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            pending = true;
+        }
+    }
     long long n = (long long)ctx->hp->count;
     ctx->n_last = n;
-    if (resync) CU(cudaMemcpyAsync(ctx->d_energy, ctx->d_energy + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     if (allreduce && ctx->g.ghost) {
 #if MC2D_HAVE_NCCL_H
         if (!ctx->have_comm) FAIL(MC2D_ERR_STATE, "allreduce requested without a communicator");
@@ -1305,9 +1328,10 @@ static int energy_on_slots(mc2d_ctx *ctx, double *U, double *W, long long *N, bo
         *U = h[0];
         *W = h[1];
         n = (long long)llround(h[2]);
+        pending = false;
 #endif
     }
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (pending) CU(cudaStreamSynchronize(ctx->stream));
     if (N) *N = n;
     return MC2D_OK;
 }
@@ -1690,8 +1714,10 @@ static int launch_sweep_p(mc2d_ctx *ctx, const SweepArgs &a, int wpb, size_t sme
     return MC2D_OK;
 }
 
+static int enqueue_stats_fetch(mc2d_ctx *ctx);
+
 static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_plan *plan, mc2d_trial *trace,
-                           long long trace_cap, long long *trace_n) {
+                           long long trace_cap, long long *trace_n, bool with_stats = false) {
     if (!ctx->have_particles) FAIL(MC2D_ERR_STATE, "no particles uploaded");
     ctx->rescale_pending = false;  // the re-bin overwrites the spare buffer
     ctx->probe_pending = 0;
@@ -2064,6 +2090,8 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     CU(cudaMemcpyAsync(ctx->hp->errv, ctx->d_err, sizeof ctx->hp->errv, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->hp->tn = 0;
     if (trace) CU(cudaMemcpyAsync(&ctx->hp->tn, ctx->d_trace_n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (with_stats)  // the caller's statistics ride on this synchronisation instead of a second one
+        if (int rc = enqueue_stats_fetch(ctx)) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
     const int *errv = ctx->hp->errv;
@@ -2106,12 +2134,17 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
     return MC2D_OK;
 }
 
-static int fetch_stats(mc2d_ctx *ctx, mc2d_stats *st) {
+// the counters, the running energy and the particle count on their way to the pinned scalars (no synchronisation)
+static int enqueue_stats_fetch(mc2d_ctx *ctx) {
     CU(cudaMemcpyAsync(ctx->hp->counters, ctx->d_counters, sizeof ctx->hp->counters, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(&ctx->hp->energy, ctx->d_energy, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    long long n = 0;
-    int rc = count_particles(ctx, &n);  // synchronises the stream
-    if (rc) return rc;
+    return count_particles_async(ctx);
+}
+
+// ... and read after the stream has been synchronised
+static void read_stats(mc2d_ctx *ctx, mc2d_stats *st) {
+    const long long n = (long long)ctx->hp->count;
+    ctx->n_last = n;
     const unsigned long long *c = ctx->hp->counters;
     const double e = ctx->hp->energy;
     for (int i = 0; i < 3; ++i) {
@@ -2122,17 +2155,20 @@ static int fetch_stats(mc2d_ctx *ctx, mc2d_stats *st) {
     st->n_particles = n;
     st->energy = e;
     st->sweeps_done = ctx->sweep;
+}
+
+static int fetch_stats(mc2d_ctx *ctx, mc2d_stats *st) {
+    if (int rc = enqueue_stats_fetch(ctx)) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    read_stats(ctx, st);
     return MC2D_OK;
 }
 
 extern "C" int mc2d_run_sweeps(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_plan *plan, mc2d_stats *st) {
     if (!ctx) return MC2D_ERR_INVALID;
-    int rc = run_sweeps_impl(ctx, nsweeps, plan, nullptr, 0, nullptr);
+    int rc = run_sweeps_impl(ctx, nsweeps, plan, nullptr, 0, nullptr, st != nullptr);
     if (rc) return rc;
-    if (st) {
-        rc = fetch_stats(ctx, st);
-        if (rc) return rc;
-    }
+    if (st) read_stats(ctx, st);
     // A refused insertion biases the ensemble (detailed balance): it is reported whether or not the caller asked for
     // the statistics, and per CALL (stats.overflow is the running total since mc2d_reset_counters).  The sweeps of this
     // call have run and the statistics are valid; the caller re-uploads with a larger cell_capacity.
