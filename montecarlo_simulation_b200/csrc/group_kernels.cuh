@@ -268,7 +268,7 @@ template <int POT, int G>
 __global__ void __launch_bounds__(256) k_energy_p(const double2 *pos, const int *cnt, const int *perm, Grid g,
                                                   PairParams pp, double r2cut, int nitems, int cap, int stride,
                                                   double *partU, double *partW, unsigned long long *pair_stats,
-                                                  int *err) {
+                                                  int *ovf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPW = 32 / G;
     const int K = g.K;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(256) k_energy_p(const double2 *pos, const int 
     }
     int Mf = nf[0] + nf[1] + nf[2] + nf[3];
     if (Mf + n_own > cap) {  // does not fit: the host falls back to the unstaged kernel
-        if (sl == 0) atomicExch(&err[3], 1);
+        if (sl == 0) atomicExch(ovf, 1);
         Mf = 0;
         n_own = 0;
     }

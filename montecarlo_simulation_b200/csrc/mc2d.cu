@@ -101,12 +101,11 @@ inline int even_up(int v, int m) { return ((v + m - 1) / m) * m; }
 struct PinnedScalars {
     int flags[4];
     int errv[8];
-    int maxcount, ovf, csr_kept, pad;
+    int maxcount, pad0, csr_kept, pad1;
     int chunk_off[8];
     unsigned long long kept, count, tn;
-    unsigned long long ps[2];
+    EnergyResult er;  // written by k_energy_finish
     unsigned long long counters[8];
-    double uw[2];
     double energy;
 };
 
@@ -176,7 +175,9 @@ struct mc2d_ctx {
     double last_sweep_ms = 0, last_energy_ms = 0;
     long long last_tests = 0, last_evals = 0;
     unsigned long long attr_set = 0;  // bitmask of k_sweep instantiations whose smem attribute is set
-    PinnedScalars *hp = nullptr;  // cudaHostAlloc
+    PinnedScalars *hp = nullptr;      // cudaHostAlloc, mapped: the finish kernels write their scalars straight into it
+    PinnedScalars *hp_dev = nullptr;  // ... through this device alias
+    FinishWords *d_fin = nullptr;     // accumulators / tickets of the finish kernels, zero between calls
     std::map<const void *, LaunchShape> launch_shapes;  // per kernel: shape whose attribute / occupancy is cached
     long long n_last = 0;             // last known particle count (sizes the neighbour staging area)
     int last_refused = 0;             // insertions refused (cell full) by the last mc2d_run_sweeps call
@@ -409,8 +410,11 @@ extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
     CU(cudaMalloc(&ctx->d_probe_sel, 2 * sizeof(int)));
     CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->dev));
     CU(cudaMalloc(&ctx->d_trace_n, sizeof(unsigned long long)));
-    CU(cudaHostAlloc(&ctx->hp, sizeof(PinnedScalars), cudaHostAllocDefault));
+    CU(cudaHostAlloc(&ctx->hp, sizeof(PinnedScalars), cudaHostAllocMapped));
     memset(ctx->hp, 0, sizeof(PinnedScalars));
+    CU(cudaHostGetDevicePointer((void **)&ctx->hp_dev, ctx->hp, 0));
+    CU(cudaMalloc(&ctx->d_fin, sizeof(FinishWords)));
+    CU(cudaMemsetAsync(ctx->d_fin, 0, sizeof(FinishWords), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_energy, 0, 4 * sizeof(double), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_err, 0, 8 * sizeof(int), ctx->stream));
@@ -469,6 +473,7 @@ extern "C" int mc2d_destroy(mc2d_ctx *ctx) {
         if (ctx->d_counters) cudaFree(ctx->d_counters);
         if (ctx->d_energy) cudaFree(ctx->d_energy);
         if (ctx->d_pair_stats) cudaFree(ctx->d_pair_stats);
+        if (ctx->d_fin) cudaFree(ctx->d_fin);
         if (ctx->d_err) cudaFree(ctx->d_err);
         if (ctx->d_work) cudaFree(ctx->d_work);
         if (ctx->d_probe) cudaFree(ctx->d_probe);
@@ -1002,11 +1007,9 @@ extern "C" int mc2d_upload_ex(mc2d_ctx *ctx, const double *xy, const int *ids, l
 static int count_particles_async(mc2d_ctx *ctx) {
     const Grid &g = ctx->g;
     const int cell0 = g.ghost * g.ny, ncell = g.ncol * g.ny;
-    CU(cudaMemsetAsync(ctx->d_pair_stats + 2, 0, sizeof(unsigned long long), ctx->stream));
-    k_sum_counts<<<(ncell + 255) / 256, 256, 0, ctx->stream>>>(ctx->cnt[ctx->cur], cell0, ncell, ctx->d_pair_stats + 2);
+    const int nb = std::max(1, std::min((ncell + 1023) / 1024, 4 * ctx->num_sms));
+    k_sum_counts<<<nb, 256, 0, ctx->stream>>>(ctx->cnt[ctx->cur], cell0, ncell, ctx->d_fin, &ctx->hp_dev->count);
     ctx->launches++;
-    CU(cudaMemcpyAsync(&ctx->hp->count, ctx->d_pair_stats + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                       ctx->stream));
     return MC2D_OK;
 }
 
@@ -1195,8 +1198,6 @@ static int launch_energy_items(mc2d_ctx *ctx, double *U, double *W, bool *done, 
     const int nparts = nblocks * wpb;  // one partial sum per warp
     CU(ctx->partial.ensure(sizeof(double) * 2 * (size_t)nparts));
     double *pU = ctx->partial.as<double>(), *pW = pU + nparts;
-    CU(cudaMemsetAsync(ctx->d_pair_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_err + 3, 0, sizeof(int), ctx->stream));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     DISPATCH_POT(ctx->prm.potential, {
         if (G == 4) {
@@ -1207,7 +1208,7 @@ static int launch_energy_items(mc2d_ctx *ctx, double *U, double *W, bool *done, 
             }
             k_energy_p<POT, 4><<<nblocks, wpb * 32, smem, ctx->stream>>>(
                 ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->order_buf.as<int>(), g, ctx->pp, ctx->r2cut, nitems, cap,
-                (int)lay.per_group, pU, pW, ctx->d_pair_stats, ctx->d_err);
+                (int)lay.per_group, pU, pW, ctx->d_fin->pair_stats, &ctx->d_fin->energy_ovf);
         } else {
             LaunchShape &ls = ctx->launch_shapes[(const void *)k_energy_p<POT, 8>];
             if (!ls.occ) {
@@ -1216,30 +1217,21 @@ static int launch_energy_items(mc2d_ctx *ctx, double *U, double *W, bool *done, 
             }
             k_energy_p<POT, 8><<<nblocks, wpb * 32, smem, ctx->stream>>>(
                 ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->order_buf.as<int>(), g, ctx->pp, ctx->r2cut, nitems, cap,
-                (int)lay.per_group, pU, pW, ctx->d_pair_stats, ctx->d_err);
+                (int)lay.per_group, pU, pW, ctx->d_fin->pair_stats, &ctx->d_fin->energy_ovf);
         }
     });
-    k_reduce_partials<<<2, 1024, 0, ctx->stream>>>(pU, nparts, 1.0, ctx->d_energy + 1, 0);  // U and W
+    // U and W in fixed order; the CTA that finishes last writes them, the pair statistics and the overflow flag into the
+    // pinned scalars and re-synchronises the running energy (unless an item overflowed its shared memory — never seen —
+    // and the caller's fallback redoes the reduction): one kernel, one stream synchronisation, no copies
+    k_energy_finish<<<2, 1024, 0, ctx->stream>>>(pU, nparts, ctx->d_energy, resync ? 1 : 0, ctx->d_fin, &ctx->hp_dev->er);
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 2;
     PinnedScalars *hp = ctx->hp;
-    CU(cudaMemcpyAsync(hp->uw, ctx->d_energy + 1, sizeof hp->uw, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(hp->ps, ctx->d_pair_stats, sizeof hp->ps, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&hp->ovf, ctx->d_err + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    // the running energy takes the recomputed value before the one synchronisation of this call; should an item have
-    // overflowed its shared memory (never seen), the running energy is restored and the caller's fallback redoes it
-    if (resync) {
-        CU(cudaMemcpyAsync(ctx->d_energy + 3, ctx->d_energy, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_energy, ctx->d_energy + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    }
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
-    if (hp->ovf) {
-        if (resync) CU(cudaMemcpyAsync(ctx->d_energy, ctx->d_energy + 3, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        return MC2D_OK;
-    }
-    const double *uw = hp->uw;
-    const unsigned long long *ps = hp->ps;
+    if (hp->er.ovf) return MC2D_OK;
+    const double *uw = hp->er.uw;
+    const unsigned long long *ps = hp->er.ps;
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_energy_ms = ms;
@@ -1714,7 +1706,7 @@ static int launch_sweep_p(mc2d_ctx *ctx, const SweepArgs &a, int wpb, size_t sme
     return MC2D_OK;
 }
 
-static int enqueue_stats_fetch(mc2d_ctx *ctx);
+static int enqueue_stats_fetch(mc2d_ctx *ctx, bool counters_too);
 
 static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_plan *plan, mc2d_trial *trace,
                            long long trace_cap, long long *trace_n, bool with_stats = false) {
@@ -2084,14 +2076,15 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
         if (rc) return rc;
         if ((rc = halo_exchange(ctx, ctx->cur, false, false, true, true, false, sa))) return rc;
     }
-    k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(ctx->partial.as<double>(), 4 * nblocks, 1.0, ctx->d_energy, 1);
+    // running energy += the batch's energy changes; error words, counters and the energy land in the pinned scalars
+    k_sweeps_finish<<<1, 1024, 0, ctx->stream>>>(ctx->partial.as<double>(), 4 * nblocks, ctx->d_energy, ctx->d_err, ctx->d_counters,
+                                                 ctx->hp_dev->errv, ctx->hp_dev->counters, &ctx->hp_dev->energy);
     ctx->launches++;
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->hp->errv, ctx->d_err, sizeof ctx->hp->errv, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->hp->tn = 0;
     if (trace) CU(cudaMemcpyAsync(&ctx->hp->tn, ctx->d_trace_n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    if (with_stats)  // the caller's statistics ride on this synchronisation instead of a second one
-        if (int rc = enqueue_stats_fetch(ctx)) return rc;
+    if (with_stats)  // the caller's statistics ride on this synchronisation (k_sweeps_finish has sent the counters)
+        if (int rc = enqueue_stats_fetch(ctx, false)) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
     const int *errv = ctx->hp->errv;
@@ -2135,9 +2128,11 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
 }
 
 // the counters, the running energy and the particle count on their way to the pinned scalars (no synchronisation)
-static int enqueue_stats_fetch(mc2d_ctx *ctx) {
-    CU(cudaMemcpyAsync(ctx->hp->counters, ctx->d_counters, sizeof ctx->hp->counters, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&ctx->hp->energy, ctx->d_energy, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+static int enqueue_stats_fetch(mc2d_ctx *ctx, bool counters_too = true) {
+    if (counters_too) {
+        CU(cudaMemcpyAsync(ctx->hp->counters, ctx->d_counters, sizeof ctx->hp->counters, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(&ctx->hp->energy, ctx->d_energy, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     return count_particles_async(ctx);
 }
 

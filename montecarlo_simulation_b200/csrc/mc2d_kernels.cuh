@@ -289,6 +289,92 @@ __global__ void __launch_bounds__(1024) k_reduce_partials(const double *part, in
     if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.0) + scale * s;
 }
 
+// Scalars that travel to the host at the end of a call are WRITTEN INTO PINNED HOST MEMORY by the last kernel that
+// produces them (the pointer is the device alias of the context's PinnedScalars): no memset before, no copy after —
+// after a stream synchronisation the GPU has been idle, so every extra tiny operation on the stream costs its full
+// submission latency.  Accumulators and tickets are left zero by the block that finishes last.
+struct FinishWords {
+    unsigned long long count_acc;  // k_sum_counts
+    unsigned int count_ticket, energy_ticket;
+    unsigned long long pair_stats[2];  // k_energy_p: pair tests, pair evaluations
+    int energy_ovf, pad;               // k_energy_p: an item did not fit its shared memory
+};
+
+// what the host reads after a reduction (lies inside PinnedScalars)
+struct EnergyResult {
+    unsigned long long ps[2];  // pair tests, pair evaluations
+    double uw[2];              // U, W
+    int ovf, pad;
+};
+
+// k_reduce_partials for the two quantities of k_energy_p (CTA 0: U -> energy[1], CTA 1: W -> energy[2]); the CTA that
+// finishes last hands everything to the host, re-synchronises the running energy (energy[0] = U) if asked and no item
+// overflowed, and re-arms the accumulators.
+__global__ void __launch_bounds__(1024) k_energy_finish(const double *part, int n, double *energy, int resync,
+                                                        FinishWords *fw, EnergyResult *out_host) {
+    __shared__ double red[32];
+    part += (size_t)blockIdx.x * n;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = threadIdx.x;
+    const int st = blockDim.x;
+    for (; i + 3 * st < n; i += 4 * st) {
+        s0 += part[i];
+        s1 += part[i + st];
+        s2 += part[i + 2 * st];
+        s3 += part[i + 3 * st];
+    }
+    for (; i < n; i += st) s0 += part[i];
+    double s = (s0 + s1) + (s2 + s3);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) {
+        energy[1 + blockIdx.x] = s;
+        __threadfence();
+        if (atomicAdd(&fw->energy_ticket, 1u) == gridDim.x - 1) {
+            __threadfence();
+            const double U = *(volatile double *)(energy + 1), W = *(volatile double *)(energy + 2);
+            const int o = fw->energy_ovf;
+            out_host->uw[0] = U;
+            out_host->uw[1] = W;
+            out_host->ps[0] = fw->pair_stats[0];
+            out_host->ps[1] = fw->pair_stats[1];
+            out_host->ovf = o;
+            if (resync && !o) energy[0] = U;
+            fw->pair_stats[0] = fw->pair_stats[1] = 0ull;
+            fw->energy_ovf = 0;
+            fw->energy_ticket = 0u;
+        }
+    }
+}
+
+// end of a sweep batch: energy[0] += sum of the per-item energy changes (fixed order), then the error words, the
+// trial counters and the running energy go to the host
+__global__ void __launch_bounds__(1024) k_sweeps_finish(const double *part, int n, double *energy, const int *err,
+                                                        const unsigned long long *counters, int *errv_host,
+                                                        unsigned long long *counters_host, double *energy_host) {
+    __shared__ double red[32];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = threadIdx.x;
+    const int st = blockDim.x;
+    for (; i + 3 * st < n; i += 4 * st) {
+        s0 += part[i];
+        s1 += part[i + st];
+        s2 += part[i + 2 * st];
+        s3 += part[i + 3 * st];
+    }
+    for (; i < n; i += st) s0 += part[i];
+    double s = (s0 + s1) + (s2 + s3);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) {
+        const double e = energy[0] + s;
+        energy[0] = e;
+        *energy_host = e;
+    }
+    if (threadIdx.x < 8) {
+        errv_host[threadIdx.x] = err[threadIdx.x];
+        counters_host[threadIdx.x] = counters[threadIdx.x];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K6 — energy of arbitrary trial points against a CSR configuration
 //   computeLocalEnergy over getNeighbors2(point) (cell_list.cpp:72-101), optional excluded particle.
@@ -762,11 +848,26 @@ __global__ void k_compact(const double2 *pos, const int *cnt, const int *ids, co
     }
 }
 
-__global__ void k_sum_counts(const int *cnt, int cell0, int ncell, unsigned long long *out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int n = (i < ncell) ? cnt[cell0 + i] : 0;
+// particles in the owned cells -> *out_host (one atomic per block; the last block exports and re-arms)
+__global__ void __launch_bounds__(256) k_sum_counts(const int *cnt, int cell0, int ncell, FinishWords *fw,
+                                                    unsigned long long *out_host) {
+    __shared__ int red[8];
+    int n = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += gridDim.x * blockDim.x) n += cnt[cell0 + i];
     n = warp_sum_int(n);
-    if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, (unsigned long long)n);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        if (s) atomicAdd(&fw->count_acc, (unsigned long long)s);
+        __threadfence();
+        if (atomicAdd(&fw->count_ticket, 1u) == gridDim.x - 1) {
+            __threadfence();
+            *out_host = atomicExch(&fw->count_acc, 0ull);
+            fw->count_ticket = 0u;
+        }
+    }
 }
 
 
