@@ -107,6 +107,7 @@ struct PinnedScalars {
     EnergyResult er;  // written by k_energy_finish
     unsigned long long counters[8];
     double energy;
+    double global_uwn[4];  // all-reduced U, W, N, overflow flag
 };
 
 struct LaunchShape {
@@ -156,7 +157,7 @@ struct mc2d_ctx {
     double rescale_Lx = 0, rescale_Ly = 0, rescale_U = 0;
 
     unsigned long long *d_counters = nullptr;  // 8
-    double *d_energy = nullptr;                // [0] running, [1] U, [2] W, [3] N
+    double *d_energy = nullptr;                // [0] running, [1] U, [2] W, [3] N, [4] k_energy_p overflowed, [5] spare
     unsigned long long *d_pair_stats = nullptr;  // 2 + [2] particle count
     int *d_err = nullptr;                      // [0] overflow need, [1] flags, [2] max count, [3] energy item did not fit,
                                                // [4] an in-kernel wait gave up (never cleared), [5] insertions refused in this call
@@ -402,7 +403,7 @@ extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
     CU(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
     for (cudaEvent_t &e : ctx->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
-    CU(cudaMalloc(&ctx->d_energy, 4 * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_energy, 6 * sizeof(double)));
     CU(cudaMalloc(&ctx->d_pair_stats, 4 * sizeof(unsigned long long)));
     CU(cudaMalloc(&ctx->d_err, 8 * sizeof(int)));
     CU(cudaMalloc(&ctx->d_work, 8 * sizeof(int)));
@@ -416,7 +417,7 @@ extern "C" int mc2d_create(const mc2d_params *p, mc2d_ctx **out) {
     CU(cudaMalloc(&ctx->d_fin, sizeof(FinishWords)));
     CU(cudaMemsetAsync(ctx->d_fin, 0, sizeof(FinishWords), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_energy, 0, 4 * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_energy, 0, 6 * sizeof(double), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_err, 0, 8 * sizeof(int), ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return MC2D_OK;
@@ -1008,7 +1009,7 @@ static int count_particles_async(mc2d_ctx *ctx) {
     const Grid &g = ctx->g;
     const int cell0 = g.ghost * g.ny, ncell = g.ncol * g.ny;
     const int nb = std::max(1, std::min((ncell + 1023) / 1024, 4 * ctx->num_sms));
-    k_sum_counts<<<nb, 256, 0, ctx->stream>>>(ctx->cnt[ctx->cur], cell0, ncell, ctx->d_fin, &ctx->hp_dev->count);
+    k_sum_counts<<<nb, 256, 0, ctx->stream>>>(ctx->cnt[ctx->cur], cell0, ncell, ctx->d_fin, &ctx->hp_dev->count, ctx->d_energy + 3);
     ctx->launches++;
     return MC2D_OK;
 }
@@ -1180,7 +1181,7 @@ static int build_order(mc2d_ctx *ctx, const SlabHalo *wait = nullptr) {
 
 // K4 on the slot layout through the sorted items (k_energy_p).  *done = false: not applicable here (tiny grid,
 // huge cells) or an item did not fit its shared memory — the caller uses k_energy_virial_g instead.
-static int launch_energy_items(mc2d_ctx *ctx, double *U, double *W, bool *done, bool resync) {
+static int launch_energy_items(mc2d_ctx *ctx, double *U, double *W, bool *done, bool resync, bool allreduce, bool *reduced) {
     *done = false;
     const Grid &g = ctx->g;
     if (g.nx < 4 || g.ny < 4) return MC2D_OK;
@@ -1227,9 +1228,25 @@ static int launch_energy_items(mc2d_ctx *ctx, double *U, double *W, bool *done, 
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 2;
     PinnedScalars *hp = ctx->hp;
+    *reduced = false;
+#if MC2D_HAVE_NCCL_H
+    if (allreduce) {  // {U, W, N, overflow} summed over the slabs on the device, behind the same synchronisation
+        if (!ctx->have_comm) FAIL(MC2D_ERR_STATE, "allreduce requested without a communicator");
+        ncclResult_t r = g_nccl.AllReduce(ctx->d_energy + 1, ctx->d_energy + 1, 4, ncclDouble, ncclSum, ctx->comm, ctx->stream);
+        if (r != ncclSuccess) FAIL(MC2D_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+        CU(cudaMemcpyAsync(hp->global_uwn, ctx->d_energy + 1, sizeof hp->global_uwn, cudaMemcpyDeviceToHost, ctx->stream));
+        *reduced = true;
+    }
+#else
+    (void)allreduce;
+#endif
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
-    if (hp->er.ovf) return MC2D_OK;
+    // (an item that overflowed its shared memory — never seen — sends EVERY rank to the fallback: the flag is summed)
+    if (hp->er.ovf || (*reduced && hp->global_uwn[3] != 0.0)) {
+        *reduced = false;
+        return MC2D_OK;
+    }
     const double *uw = hp->er.uw;
     const unsigned long long *ps = hp->er.ps;
     float ms = 0;
@@ -1294,7 +1311,9 @@ static int energy_on_slots(mc2d_ctx *ctx, double *U, double *W, long long *N, bo
     int rc = MC2D_OK;
     // the particle count rides on the synchronisation of the energy launch
     if ((rc = count_particles_async(ctx))) return rc;
-    if (!ctx->tune.energy_unstaged) rc = launch_energy_items(ctx, U, W, &done, resync);
+    const bool want_global = allreduce && ctx->g.ghost;
+    bool reduced = false;
+    if (!ctx->tune.energy_unstaged) rc = launch_energy_items(ctx, U, W, &done, resync, want_global, &reduced);
     if (rc) return rc;
     bool pending = false;  // work on the stream behind the last synchronisation
     if (!done) {
@@ -1307,7 +1326,11 @@ static int energy_on_slots(mc2d_ctx *ctx, double *U, double *W, long long *N, bo
     }
     long long n = (long long)ctx->hp->count;
     ctx->n_last = n;
-    if (allreduce && ctx->g.ghost) {
+    if (want_global && reduced) {
+        *U = ctx->hp->global_uwn[0];
+        *W = ctx->hp->global_uwn[1];
+        n = (long long)llround(ctx->hp->global_uwn[2]);
+    } else if (want_global) {
 #if MC2D_HAVE_NCCL_H
         if (!ctx->have_comm) FAIL(MC2D_ERR_STATE, "allreduce requested without a communicator");
         double h[3] = {*U, *W, (double)n};

@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(1024) k_energy_finish(const double *part, int 
             out_host->ps[0] = fw->pair_stats[0];
             out_host->ps[1] = fw->pair_stats[1];
             out_host->ovf = o;
+            energy[4] = (double)o;  // all-reduced with U, W, N: every rank learns whether ANY rank must fall back
             if (resync && !o) energy[0] = U;
             fw->pair_stats[0] = fw->pair_stats[1] = 0ull;
             fw->energy_ovf = 0;
@@ -850,7 +851,7 @@ __global__ void k_compact(const double2 *pos, const int *cnt, const int *ids, co
 
 // particles in the owned cells -> *out_host (one atomic per block; the last block exports and re-arms)
 __global__ void __launch_bounds__(256) k_sum_counts(const int *cnt, int cell0, int ncell, FinishWords *fw,
-                                                    unsigned long long *out_host) {
+                                                    unsigned long long *out_host, double *out_dev) {
     __shared__ int red[8];
     int n = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += gridDim.x * blockDim.x) n += cnt[cell0 + i];
@@ -864,7 +865,9 @@ __global__ void __launch_bounds__(256) k_sum_counts(const int *cnt, int cell0, i
         __threadfence();
         if (atomicAdd(&fw->count_ticket, 1u) == gridDim.x - 1) {
             __threadfence();
-            *out_host = atomicExch(&fw->count_acc, 0ull);
+            const unsigned long long total = atomicExch(&fw->count_acc, 0ull);
+            *out_host = total;
+            *out_dev = (double)total;  // energy[3]: rides in the all-reduce of {U, W, N, overflow}
             fw->count_ticket = 0u;
         }
     }
