@@ -170,8 +170,11 @@ __global__ void __launch_bounds__(256) k_rebin_g(const double2 *pos_o, const int
 }
 
 // K1', common case (rebin4_cells, sweep_kernel_p.cuh): exactly 4 old cells can hold particles of a new cell.
+#ifndef MC2D_REBIN_HALO_BLOCKS
+#define MC2D_REBIN_HALO_BLOCKS 6
+#endif
 template <int G, bool HALO>
-__global__ void __launch_bounds__(256, 6) k_rebin4(const double2 *pos_o, const int *cnt_o, const int *ids_o,
+__global__ void __launch_bounds__(256, HALO ? MC2D_REBIN_HALO_BLOCKS : 6) k_rebin4(const double2 *pos_o, const int *cnt_o, const int *ids_o,
                                                 double2 *pos_n, int *cnt_n, int *ids_n, Grid gn, int sx, int sy,
                                                 int w0, int n0, int w1, int n1, int *err, SlabHalo sh) {
     constexpr int GPW = 32 / G;

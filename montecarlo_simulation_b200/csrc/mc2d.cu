@@ -1867,8 +1867,9 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             sh.hflag[side] = reinterpret_cast<unsigned long long *>(pb) + (side == 0 ? 1 : 0);
         }
         sh.bcount = ctx->d_work + 7;
-        const long long last0 = (long long)(g.ncol - 1) * g.ny, end = (long long)g.ncol * g.ny;
-        sh.nbwarps = (g.ny + 7) / 8 + (int)((end + 7) / 8 - last0 / 8);
+        // k_rebin4 is launched with the last owned column first and the first owned column right behind it (see below):
+        // the cells of the two slab-edge columns are the first 2 ny cells of its list, 8 cells per warp
+        sh.nbwarps = (2 * g.ny + 7) / 8;
         sh.err = ctx->d_err;
         sh.spin_budget_ns = spin_budget_ns(ctx);
         return sh;
@@ -1890,10 +1891,16 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             CU(cudaMemsetAsync(ctx->d_work + 7, 0, sizeof(int), sa));
             int rc = ktime_begin(ctx, 1);
             if (rc) return rc;
+#ifdef MC2D_PROBE_REBIN_PLAIN
+            k_rebin4<4, false><<<(ncell_owned + 63) / 64, 256, 0, sa>>>(
+#else
             k_rebin4<4, true><<<(ncell_owned + 63) / 64, 256, 0, sa>>>(
+#endif
                 ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->use_ids ? ctx->ids[ctx->cur] : nullptr, ctx->pos[nb], ctx->cnt[nb],
-                ctx->use_ids ? ctx->ids[nb] : nullptr, gn, sx > g.ox ? 1 : -1, sy > g.oy ? 1 : -1, 0, ncell_owned, 0, 0,
-                ctx->d_err, sh);
+                ctx->use_ids ? ctx->ids[nb] : nullptr, gn, sx > g.ox ? 1 : -1, sy > g.oy ? 1 : -1,
+                // slab-edge columns first: their pushes over NVLink and the signal to the neighbours (whose k_order_local
+                // waits for it) travel while the interior columns are re-binned
+                (g.ncol - 1) * g.ny, g.ny, 0, (g.ncol - 1) * g.ny, ctx->d_err, sh);
             ctx->launches++;
             CU(cudaGetLastError());
             if ((rc = ktime_end(ctx))) return rc;

@@ -240,6 +240,7 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
     // slab edge: 0 = first owned column (goes to the left neighbour), 1 = last owned column, -1 = interior
     const int hs = (HALO && has) ? (lcx == gn.ghost ? 0 : (lcx == gn.ghost + gn.ncol - 1 ? 1 : -1)) : -1;
     const bool bwarp = HALO && __any_sync(FULL_MASK, hs >= 0);
+#ifndef MC2D_PROBE_NOWAIT
     if (bwarp) {  // the old ghost columns must be complete before this warp reads them
         if (lane == 0) {
             spin_until_ge(sh.myflag + 0, sh.wait_seq, sh.err, sh.spin_budget_ns, 6000);
@@ -248,6 +249,7 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
         }
         __syncwarp();
     }
+#endif
     int tc[4], ts[5];
     ts[0] = 0;
 #pragma unroll
@@ -259,7 +261,9 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
         }
         if (ocy < 0) ocy += gn.ny; else if (ocy >= gn.ny) ocy -= gn.ny;
         tc[c] = ocx * gn.ny + ocy;
-        ts[c + 1] = ts[c] + (has ? (bwarp ? __ldcg(&cnt_o[tc[c]]) : cnt_o[tc[c]]) : 0);
+        // (explicit ld.global.nc for the others: with an ld.global.cg on the same pointer in sight the compiler no
+        // longer proves the buffer read-only, and plain loads made the whole kernel 10 us slower)
+        ts[c + 1] = ts[c] + (has ? (bwarp ? __ldcg(&cnt_o[tc[c]]) : __ldg(&cnt_o[tc[c]])) : 0);
     }
     const int M = ts[4];
     const int KM = warp_max_int(M);
@@ -276,7 +280,7 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
             const int cc = q == 0 ? tc[0] : (q == 1 ? tc[1] : (q == 2 ? tc[2] : tc[3]));
             const int cs = q == 0 ? 0 : (q == 1 ? ts[1] : (q == 2 ? ts[2] : ts[3]));
             src = (size_t)cc * K + (k - cs);
-            p = bwarp ? __ldcg(&pos_o[src]) : pos_o[src];  // (a ghost cell: written by the neighbour, read past the L1)
+            p = bwarp ? __ldcg(&pos_o[src]) : __ldg(&pos_o[src]);  // (a ghost cell: written by the neighbour, read past the L1)
             int ngx, ncy;
             sweep_cell_of(gn, p.x, p.y, ngx, ncy);
             take = (ngx == gcx && ncy == cy);
@@ -286,8 +290,9 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
             const int off = nout + __popc(m & lt);
             if (off < K) {
                 pos_n[obase + off] = p;
-                const int id = ids_n ? (bwarp ? __ldcg(&ids_o[src]) : ids_o[src]) : 0;
+                const int id = ids_n ? (bwarp ? __ldcg(&ids_o[src]) : __ldg(&ids_o[src])) : 0;
                 if (ids_n) ids_n[obase + off] = id;
+#ifndef MC2D_PROBE_NOPUSH
                 if (hs >= 0) {  // ... and into the neighbour's ghost column of the new buffer
                     // (no dynamic index into the kernel parameters: that would copy the struct to local memory)
                     double2 *hp = hs == 0 ? sh.hpos[0] : sh.hpos[1];
@@ -297,6 +302,7 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
                         hi[(size_t)cy * K + off] = id;
                     }
                 }
+#endif
             }
         }
         nout += __popc(m);
@@ -310,7 +316,9 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
         if (nout > K) atomicMax(&err[0], nout);
     }
     if (bwarp) {  // one more boundary warp done; the last one signals both neighbours
+#ifndef MC2D_PROBE_NOFENCE
         __threadfence_system();
+#endif
         __syncwarp();
         if (lane == 0 && atomicAdd(sh.bcount, 1) == sh.nbwarps - 1) {
             __threadfence_system();
@@ -521,6 +529,7 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         }
     };
     const unsigned div_i = (unsigned)ipp, div_i_inv = 0xFFFFFFFFu / div_i;
+    auto colour_of = [&](int psv) { return a.npass > 1 ? a.colours[psv] : a.colour; };
     // pass of an item: the loop variable, or (pipeline) the colour-major position in the list of all four colours
     auto pass_of = [&](int item, int ps_loop) {
         return a.pipeline ? (int)(item >= a.nitems) + (int)(item >= 2 * a.nitems) + (int)(item >= 3 * a.nitems) : ps_loop;
@@ -537,6 +546,11 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
             }
             p = (int)q;
             r = (int)rem;
+            // slab: the slab-edge pair of the pass goes first (pair 0 is there already; for odd active columns the
+            // last pair is rotated to the front).  Its items then finish about one pass before the neighbour's next
+            // pass asks for them instead of just in time; their own local dependencies (the last pairs of the
+            // previous pass) hold them up for one item at most, because tickets are handed out in order.
+            if (a.halo_fused && (colour_of(psv) & 1)) p = (q == 0) ? npairs - 1 : (int)q - 1;
         } else if (a.halo_fused) {
             if (item < ipp) {
                 p = bpair;
@@ -553,7 +567,6 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
         }
     };
     const int n_all = a.pipeline ? a.npass * a.nitems : a.nitems;
-    auto colour_of = [&](int psv) { return a.npass > 1 ? a.colours[psv] : a.colour; };
     // -> acy of this group's cell (or -1); the item's pass, pair and rank
     auto load_perm = [&](int item, int ps_loop, int &psv, int &p, int &r) {
         psv = item < n_all ? pass_of(item, ps_loop) : ps_loop;
