@@ -1891,11 +1891,7 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
             CU(cudaMemsetAsync(ctx->d_work + 7, 0, sizeof(int), sa));
             int rc = ktime_begin(ctx, 1);
             if (rc) return rc;
-#ifdef MC2D_PROBE_REBIN_PLAIN
-            k_rebin4<4, false><<<(ncell_owned + 63) / 64, 256, 0, sa>>>(
-#else
             k_rebin4<4, true><<<(ncell_owned + 63) / 64, 256, 0, sa>>>(
-#endif
                 ctx->pos[ctx->cur], ctx->cnt[ctx->cur], ctx->use_ids ? ctx->ids[ctx->cur] : nullptr, ctx->pos[nb], ctx->cnt[nb],
                 ctx->use_ids ? ctx->ids[nb] : nullptr, gn, sx > g.ox ? 1 : -1, sy > g.oy ? 1 : -1,
                 // slab-edge columns first: their pushes over NVLink and the signal to the neighbours (whose k_order_local

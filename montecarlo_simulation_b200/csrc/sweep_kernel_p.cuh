@@ -240,7 +240,6 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
     // slab edge: 0 = first owned column (goes to the left neighbour), 1 = last owned column, -1 = interior
     const int hs = (HALO && has) ? (lcx == gn.ghost ? 0 : (lcx == gn.ghost + gn.ncol - 1 ? 1 : -1)) : -1;
     const bool bwarp = HALO && __any_sync(FULL_MASK, hs >= 0);
-#ifndef MC2D_PROBE_NOWAIT
     if (bwarp) {  // the old ghost columns must be complete before this warp reads them
         if (lane == 0) {
             spin_until_ge(sh.myflag + 0, sh.wait_seq, sh.err, sh.spin_budget_ns, 6000);
@@ -249,7 +248,6 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
         }
         __syncwarp();
     }
-#endif
     int tc[4], ts[5];
     ts[0] = 0;
 #pragma unroll
@@ -292,7 +290,6 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
                 pos_n[obase + off] = p;
                 const int id = ids_n ? (bwarp ? __ldcg(&ids_o[src]) : __ldg(&ids_o[src])) : 0;
                 if (ids_n) ids_n[obase + off] = id;
-#ifndef MC2D_PROBE_NOPUSH
                 if (hs >= 0) {  // ... and into the neighbour's ghost column of the new buffer
                     // (no dynamic index into the kernel parameters: that would copy the struct to local memory)
                     double2 *hp = hs == 0 ? sh.hpos[0] : sh.hpos[1];
@@ -302,7 +299,6 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
                         hi[(size_t)cy * K + off] = id;
                     }
                 }
-#endif
             }
         }
         nout += __popc(m);
@@ -316,9 +312,7 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
         if (nout > K) atomicMax(&err[0], nout);
     }
     if (bwarp) {  // one more boundary warp done; the last one signals both neighbours
-#ifndef MC2D_PROBE_NOFENCE
         __threadfence_system();
-#endif
         __syncwarp();
         if (lane == 0 && atomicAdd(sh.bcount, 1) == sh.nbwarps - 1) {
             __threadfence_system();
