@@ -102,7 +102,7 @@ def ncu_summary(tag, rep):
                     to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
     out = {"source": os.path.basename(rep), "dram_bytes_per_launch": traffic}
     for k, v in traffic.items():
-        if k.startswith("k_sweep"):
+        if k.startswith("k_sweep_p") or k.startswith("k_sweep<"):  # not k_sweeps_finish
             out["k_sweep_dram_bytes_per_launch"] = v
     json.dump(out, open(os.path.join(PROF, "traffic_%s.json" % tag), "w"), indent=1)
 
