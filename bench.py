@@ -168,6 +168,28 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class _native_stdout_to_stderr:
+    """The reference's classes print progress and warnings with std::cout ("cell list update frequency is too high!");
+    while its code runs, file descriptor 1 points at stderr so that stdout carries nothing but the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+
+            ctypes.CDLL(None).fflush(None)  # the C++ side buffers when stdout is not a terminal
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def reference_arm(args):
     """The reference's own CPU implementation of the path (oracle/_ref = unmodified serial_src compiled in place; the
     oracle port if that .so is absent) on one host core — the serial reference is single-threaded.
@@ -179,6 +201,12 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    with _native_stdout_to_stderr():
+        line = _reference_arm_line(args)
+    print(json.dumps(line))
+
+
+def _reference_arm_line(args):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
 
@@ -235,7 +263,7 @@ def reference_arm(args):
         "run_stock": run_stock, "cpu_baseline_mpi": mpi_baseline(args),
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    return line
 
 
 def mpi_baseline(args, ranks=(1, 2, 4, 8), n_part=10_000, sweeps=2):
@@ -637,11 +665,12 @@ def main():
         sample_n = 200_000
         wl_s = workload(1, 0, sample_n)
         if ol.have_ref():
-            ref = ol.Ref()
-            mcr = ref.mc(wl_s["L"], wl_s["L"], wl_s["xy"], T=T_BENCH, ptype=ptype, rcut=rcut, mu=z_act,
-                         delta=DELTA, ensemble=ol.GCMC, seed=42)
-            secs, mv = ref.time_moves(mcr, 25, 10, True)
-            es, Ur, Wr = ref.time_energy_virial(wl_s["L"], wl_s["L"], wl_s["xy"], T=T_BENCH, ptype=ptype, rcut=rcut)
+            with _native_stdout_to_stderr():
+                ref = ol.Ref()
+                mcr = ref.mc(wl_s["L"], wl_s["L"], wl_s["xy"], T=T_BENCH, ptype=ptype, rcut=rcut, mu=z_act,
+                             delta=DELTA, ensemble=ol.GCMC, seed=42)
+                secs, mv = ref.time_moves(mcr, 25, 10, True)
+                es, Ur, Wr = ref.time_energy_virial(wl_s["L"], wl_s["L"], wl_s["xy"], T=T_BENCH, ptype=ptype, rcut=rcut)
             kind = "reference"
             # the GPU calculator hook on the same 200k-particle sample against the reference's numbers
             with m.Context(wl_s["L"], wl_s["L"], rcut, potential=args.potential, T=T_BENCH, device=local) as cc:
