@@ -261,24 +261,30 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
         tc[c] = ocx * gn.ny + ocy;
         // (explicit ld.global.nc for the others: with an ld.global.cg on the same pointer in sight the compiler no
         // longer proves the buffer read-only, and plain loads made the whole kernel 10 us slower)
-        ts[c + 1] = ts[c] + (has ? (bwarp ? __ldcg(&cnt_o[tc[c]]) : __ldg(&cnt_o[tc[c]])) : 0);
+        ts[c + 1] = ts[c] + (has ? (!HALO ? cnt_o[tc[c]] : (bwarp ? __ldcg(&cnt_o[tc[c]]) : __ldg(&cnt_o[tc[c]]))) : 0);
     }
     const int M = ts[4];
     const int KM = warp_max_int(M);
     const unsigned gmask = ((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << (gi * G);
     const unsigned lt = (1u << lane) - 1u;
     int nout = 0;
-    for (int k0 = 0; k0 < KM; k0 += G) {
-        const int k = k0 + sl;
+    // One round = G candidates per new cell: fetch (index -> old slot -> position), then test / vote / place.  TWO rounds
+    // are fetched before the first is placed, so two loads per lane are in flight (the compiler interleaves like this
+    // by itself only for the plain-load instantiation, where it is worth 4 us of 35; with the .cg / .nc intrinsics and
+    // the peer stores in the loop it has to be written out).
+    auto fetch = [&](int k, size_t &src, double2 &p) {
+        if (k >= M) return false;
+        const int q = (k >= ts[1]) + (k >= ts[2]) + (k >= ts[3]);
+        const int cc = q == 0 ? tc[0] : (q == 1 ? tc[1] : (q == 2 ? tc[2] : tc[3]));
+        const int cs = q == 0 ? 0 : (q == 1 ? ts[1] : (q == 2 ? ts[2] : ts[3]));
+        src = (size_t)cc * K + (k - cs);
+        // (a ghost cell: written by the neighbour, read past the L1)
+        p = !HALO ? pos_o[src] : (bwarp ? __ldcg(&pos_o[src]) : __ldg(&pos_o[src]));
+        return true;
+    };
+    auto place = [&](bool valid, size_t src, double2 p) {
         bool take = false;
-        double2 p = make_double2(0.0, 0.0);
-        size_t src = 0;
-        if (k < M) {
-            const int q = (k >= ts[1]) + (k >= ts[2]) + (k >= ts[3]);
-            const int cc = q == 0 ? tc[0] : (q == 1 ? tc[1] : (q == 2 ? tc[2] : tc[3]));
-            const int cs = q == 0 ? 0 : (q == 1 ? ts[1] : (q == 2 ? ts[2] : ts[3]));
-            src = (size_t)cc * K + (k - cs);
-            p = bwarp ? __ldcg(&pos_o[src]) : __ldg(&pos_o[src]);  // (a ghost cell: written by the neighbour, read past the L1)
+        if (valid) {
             int ngx, ncy;
             sweep_cell_of(gn, p.x, p.y, ngx, ncy);
             take = (ngx == gcx && ncy == cy);
@@ -288,7 +294,7 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
             const int off = nout + __popc(m & lt);
             if (off < K) {
                 pos_n[obase + off] = p;
-                const int id = ids_n ? (bwarp ? __ldcg(&ids_o[src]) : __ldg(&ids_o[src])) : 0;
+                const int id = ids_n ? (!HALO ? ids_o[src] : (bwarp ? __ldcg(&ids_o[src]) : __ldg(&ids_o[src]))) : 0;
                 if (ids_n) ids_n[obase + off] = id;
                 if (hs >= 0) {  // ... and into the neighbour's ghost column of the new buffer
                     // (no dynamic index into the kernel parameters: that would copy the struct to local memory)
@@ -302,6 +308,20 @@ __device__ __forceinline__ void rebin4_cells(const double2 *__restrict__ pos_o, 
             }
         }
         nout += __popc(m);
+    };
+    int k0 = 0;
+    for (; k0 + G < KM; k0 += 2 * G) {
+        size_t src_a = 0, src_b = 0;
+        double2 pa = make_double2(0.0, 0.0), pb = pa;
+        const bool va = fetch(k0 + sl, src_a, pa), vb = fetch(k0 + G + sl, src_b, pb);
+        place(va, src_a, pa);
+        place(vb, src_b, pb);
+    }
+    if (k0 < KM) {
+        size_t src_a = 0;
+        double2 pa = make_double2(0.0, 0.0);
+        const bool va = fetch(k0 + sl, src_a, pa);
+        place(va, src_a, pa);
     }
     if (has && sl == 0) {
         cnt_n[lcx * gn.ny + cy] = min(nout, K);
@@ -340,6 +360,9 @@ __device__ __forceinline__ double group_sum(double v) {
 }
 
 // (unrolling the candidate loops does not pay: 49.2 us per colour pass of config #4 without, 50.3 us x2, 54.0 us x4)
+#ifndef MC2D_SHARE_GC_BATCH
+#define MC2D_SHARE_GC_BATCH 1
+#endif
 #ifndef MC2D_HOT_UNROLL
 #define MC2D_HOT_UNROLL 1
 #endif
@@ -795,12 +818,18 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
             double batchE = 0.0;
 
             // ---- K2: displacement rounds (MC.cpp:96-123); one trial per group per round ----
+            const int T_disp = warp_max_int(n_disp);
+            // A batch of Philox words covers G trials.  When the displacement rounds do not fill their last batch and
+            // there is one grand-canonical draw per visit, the first spare sub-lane draws the words of THAT trial
+            // (same stream, same counter as the batch of its own it would otherwise get): one Philox block per item
+            // instead of two for three items in four.
+            const bool share_gc = MC2D_SHARE_GC_BATCH && a.n_gc == 1 && (T_disp & (G - 1)) != 0;
             {
-                const int T = warp_max_int(n_disp);
+                const int T = T_disp;
                 for (int t = 0; t < T; ++t) {
                     if ((t & (G - 1)) == 0) {  // sub-lane s draws the words of trial t + s of its cell's stream
-                        batch = philox4x32_10(cell_gid, MC2D_TAG_DISP | (uint32_t)(t + sl), a.sweep_lo, a.sweep_hi,
-                                              a.seed_lo, a.seed_hi);
+                        const uint32_t tag = (share_gc && t + sl == T) ? (MC2D_TAG_GC | 0u) : (MC2D_TAG_DISP | (uint32_t)(t + sl));
+                        batch = philox4x32_10(cell_gid, tag, a.sweep_lo, a.sweep_hi, a.seed_lo, a.seed_hi);
                         batchE = mc2d_exp_variate(batch.w);  // -ln u of that trial: off the critical path
                     }
                     const int src = src_base + (t & (G - 1));
@@ -874,12 +903,13 @@ __global__ void __launch_bounds__(MC2D_SWEEPP_THREADS, MC2D_SWEEPP_MIN_BLOCKS) k
             {
                 const int T = warp_max_int(n_gc);
                 for (int t = 0; t < T; ++t) {
-                    if ((t & (G - 1)) == 0) {
+                    if ((t & (G - 1)) == 0 && !share_gc) {
                         batch = philox4x32_10(cell_gid, MC2D_TAG_GC | (uint32_t)(t + sl), a.sweep_lo, a.sweep_hi,
                                               a.seed_lo, a.seed_hi);
                         batchE = mc2d_exp_variate(batch.w);
                     }
-                    const int src = src_base + (t & (G - 1));
+                    // (share_gc: T = 1 and the words sit in the first spare sub-lane of the last displacement batch)
+                    const int src = src_base + (share_gc ? (T_disp & (G - 1)) : (t & (G - 1)));
                     const uint32_t rx = __shfl_sync(FULL_MASK, batch.x, src), ry = __shfl_sync(FULL_MASK, batch.y, src);
                     const uint32_t rz = __shfl_sync(FULL_MASK, batch.z, src);
                     const double Et = __shfl_sync(FULL_MASK, batchE, src);
