@@ -1160,7 +1160,8 @@ static SlabHalo no_slab_halo() {
     return sh;
 }
 
-static int build_order(mc2d_ctx *ctx, const SlabHalo *wait = nullptr) {
+static int build_order(mc2d_ctx *ctx, const SlabHalo *wait = nullptr, int *zero_work = nullptr, int n_work = 0,
+                       int *zero_done = nullptr, int n_done = 0) {
     const Grid &g = ctx->g;
     const int ncell = g.ncol * g.ny;
     const size_t smem = sizeof(int) * (size_t)(3 * g.ny + g.ny / 2);
@@ -1172,7 +1173,8 @@ static int build_order(mc2d_ctx *ctx, const SlabHalo *wait = nullptr) {
     }
     CU(ctx->order_buf.ensure(sizeof(int) * (size_t)ncell));
     k_order_local<<<dim3(g.ncol / 2, 4), ORDL_WARPS * 32, smem, ctx->stream>>>(g, ctx->cnt[ctx->cur], ctx->order_buf.as<int>(),
-                                                                                  wait ? *wait : no_slab_halo());
+                                                                                  wait ? *wait : no_slab_halo(), zero_work,
+                                                                                  n_work, zero_done, n_done);
     ctx->launches++;
     ctx->order_valid = true;
     return MC2D_OK;
@@ -1944,12 +1946,18 @@ static int run_sweeps_impl(mc2d_ctx *ctx, long long nsweeps, const mc2d_sweep_pl
         if (persistent) {
             if (overlap && used_sb)  // the boundary stream may still be using the counters and the order of the last sweep
                 if (int rc = join()) return rc;
-            if (!ctx->order_valid)
-                if (int rc = build_order(ctx, order_wait.on ? &order_wait : nullptr)) return rc;
-            CU(cudaMemsetAsync(ctx->d_work, 0, 8 * sizeof(int), ctx->stream));
-            // finished items per (colour pass, column pair) + 8 words of the slab pipeline (edge items per pass, frontier)
-            CU(ctx->done_buf.ensure(sizeof(int) * (4 * (size_t)npairs + 8)));
-            CU(cudaMemsetAsync(ctx->done_buf.p, 0, sizeof(int) * (4 * (size_t)npairs + 8), ctx->stream));
+            // ticket counters; finished items per (colour pass, column pair) + 8 words of the slab pipeline (edge items per
+            // pass, frontier): zero before the sweep kernel — by k_order_local when it runs anyway (every sweep with a grid
+            // shift), by two memsets otherwise
+            const int n_done = 4 * npairs + 8;
+            CU(ctx->done_buf.ensure(sizeof(int) * (size_t)n_done));
+            if (!ctx->order_valid) {
+                if (int rc = build_order(ctx, order_wait.on ? &order_wait : nullptr, ctx->d_work, 8, ctx->done_buf.as<int>(), n_done))
+                    return rc;
+            } else {
+                CU(cudaMemsetAsync(ctx->d_work, 0, 8 * sizeof(int), ctx->stream));
+                CU(cudaMemsetAsync(ctx->done_buf.p, 0, sizeof(int) * (size_t)n_done, ctx->stream));
+            }
         }
         // slab mode: the same single launch, with the halo exchange inside the kernel (boundary items wait on the
         // neighbour's flag word, push their cells into its ghost column, the last one signals)

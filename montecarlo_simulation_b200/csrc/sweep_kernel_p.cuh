@@ -209,10 +209,18 @@ __device__ __forceinline__ void order_local_task(const Grid &g, const int *cnt, 
 }
 
 // dynamic shared memory: 3 columns x ny counts, then nay keys
-__global__ void __launch_bounds__(ORDL_WARPS * 32) k_order_local(Grid g, const int *cnt, int *perm, SlabHalo sh) {
+// zero_work / zero_done (optional): the sweep kernel's ticket counters and completion counters, which the launch that
+// follows this one on the stream expects to be zero — cleared here instead of by two memsets between the kernels.
+__global__ void __launch_bounds__(ORDL_WARPS * 32) k_order_local(Grid g, const int *cnt, int *perm, SlabHalo sh,
+                                                                 int *zero_work, int n_work, int *zero_done, int n_done) {
     extern __shared__ int ol_smem[];
     __shared__ int wc[ORDL_WARPS * ORDL_BINS];
     __shared__ int bin_base[ORDL_BINS];
+    {
+        const int cta = blockIdx.y * gridDim.x + blockIdx.x, nthreads = gridDim.x * gridDim.y * blockDim.x;
+        for (int i = cta * blockDim.x + threadIdx.x; i < n_done; i += nthreads) zero_done[i] = 0;
+        if (cta == 0 && (int)threadIdx.x < n_work) zero_work[threadIdx.x] = 0;
+    }
     order_local_task<ORDL_WARPS>(g, cnt, perm, blockIdx.x, blockIdx.y, ol_smem, wc, bin_base, sh);
 }
 
