@@ -213,7 +213,7 @@ def _reference_arm_line(args):
     rcut, z, _ = POTENTIALS[args.potential]
     ptype = {"LennardJones": ol.LJ, "WCA": ol.WCA}[args.potential]
     per_gpu = args.particles_per_gpu or default_per_gpu(args.gpus)
-    sample_n = 1_000_000
+    sample_n = args.ref_sample_particles
     wl = workload(1, 0, sample_n)
     L, xy = wl["L"], wl["xy"]
     run_stock = None
@@ -260,7 +260,8 @@ def _reference_arm_line(args):
         "cpu_baseline": {"value": value, "unit": "moves/s", "cores": 1, "kind": kind, "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": value, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "run_stock": run_stock, "cpu_baseline_mpi": mpi_baseline(args),
+        "run_stock": run_stock,
+        "cpu_baseline_mpi": {"skipped": "--no-mpi-baseline"} if args.no_mpi_baseline else mpi_baseline(args),
         "gpu_launches": 0,
     }
     return line
@@ -392,6 +393,9 @@ def main():
     ap.add_argument("--no-extra-legs", action="store_true", help="skip nselect2 / weak_ref_2000k / WCA side measurements")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--equil-sweeps", type=int, default=300)
+    ap.add_argument("--ref-sample-particles", type=int, default=1_000_000,
+                    help="--impl reference: particles in the cut of the workload one step sweeps (tests use a small one)")
+    ap.add_argument("--no-mpi-baseline", action="store_true", help="skip the reference-MPI-on-shim side measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
