@@ -1,7 +1,8 @@
 // slab_traj_selftest — writes the frames of traj_cases.hpp through LoggingTrajSlabs in every file mode, with
 // forked ranks exactly as mc2d_slabs starts them (no GPU involved): `slab_traj_selftest <nranks> <outdir>`.
 // Files: <outdir>/{perrank,gather,mpiio}{,_typed}.{xyz,dump} (+ .rankNNNN for the per-rank mode) and, for the
-// append option, <outdir>/append_{gather,mpiio}.dump (two loggers in a row, the second appending).
+// append option, <outdir>/append_{gather,mpiio}.dump (two loggers in a row, the second appending).  Also the serial
+// Logging class's position files, <outdir>/serial.{xyz,dump} (frames of rank 0, 2, 0).
 #include <sys/mman.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -63,6 +64,16 @@ int main(int argc, char **argv) {
     }
     const int size = std::atoi(argv[1]);
     if (size < 1 || size > mc2d_slabs::kMaxRanks) return 1;
+    {   // the serial logger's position files (Logging, logging.cpp:30-79): frames of "ranks" 0 and 2
+        const std::string dir = argv[2];
+        SimulationBox box(traj_cases::kLx, traj_cases::kLy);
+        Logging xyz(dir + "/serial.xyz", dir + "/serial_xyz.dat"), dump(dir + "/serial.dump", dir + "/serial_dump.dat");
+        for (int f = 0; f < traj_cases::kFrames; ++f) {
+            const std::vector<Particle> p = particles(f == 1 ? 2 : 0, f);
+            xyz.logPositions_xyz(p, box, 6.25);
+            dump.logPositions_dump(p, box, traj_cases::timestep(f));
+        }
+    }
     void *mem = mmap(nullptr, sizeof(Shared), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
     if (mem == MAP_FAILED) return 2;
     Shared *sh = new (mem) Shared();

@@ -316,4 +316,26 @@ double ref_time_energy_virial(double T, int type, double rcut, double f, double 
     return std::chrono::duration<double>(b - a).count();
 }
 
+// The reference's position logs (logging.cpp:30-79) for `nframes` frames lying behind each other in xy (counts[f]
+// particles each): dump != 0 -> logPositions_dump with timesteps[f], else logPositions_xyz.  Golden side of
+// tests/test_traj_logger.py::test_serial_position_logs.
+int ref_log_positions(const char *path_pos, const char *path_data, int dump, double Lx, double Ly, const double *xy,
+                      const int *counts, int nframes, const int *timesteps) {
+    try {
+        Logging log(path_pos, path_data);
+        SimulationBox box(Lx, Ly);
+        size_t at = 0;
+        for (int f = 0; f < nframes; ++f) {
+            std::vector<Particle> P = to_particles(xy + 2 * at, counts[f]);
+            at += (size_t)counts[f];
+            if (dump) log.logPositions_dump(P, box, timesteps[f]);
+            else log.logPositions_xyz(P, box, 0.0);
+        }
+        log.close();
+        return 0;
+    } catch (...) {
+        return 1;
+    }
+}
+
 }  // extern "C"

@@ -352,6 +352,17 @@ class Ref:
         L.ref_time_moves.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, i, c_ll_p]
         L.ref_time_energy_virial.restype = d
         L.ref_time_energy_virial.argtypes = [d, i, d, d, d, d, d, d, d, c_double_p, i, c_double_p, c_double_p]
+        if hasattr(L, "ref_log_positions"):
+            L.ref_log_positions.argtypes = [C.c_char_p, C.c_char_p, i, d, d, c_double_p, C.POINTER(C.c_int), i, C.POINTER(C.c_int)]
+
+    def log_positions(self, path_pos, path_data, dump, Lx, Ly, frames, timesteps):
+        """the reference's Logging::logPositions_xyz / _dump (logging.cpp:30-79) for a list of (n, 2) frames"""
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(f, dtype=np.float64).reshape(-1, 2) for f in frames]))
+        counts = np.array([len(f) for f in frames], dtype=np.int32)
+        ts = np.array(timesteps, dtype=np.int32)
+        rc = self.lib.ref_log_positions(str(path_pos).encode(), str(path_data).encode(), int(dump), Lx, Ly, _dp(flat),
+                                        counts.ctypes.data_as(C.POINTER(C.c_int)), len(frames), ts.ctypes.data_as(C.POINTER(C.c_int)))
+        assert rc == 0
 
     def observable(self, what, Lx, Ly, xy, *, T=1.0, press=0.0, ptype=LJ, rcut=2.5, mu=0.0, f=0.0, alpha=0.0,
                    A0=0.0, kappa=0.0):

@@ -29,7 +29,7 @@ def run(binary, nranks, outdir):
 
 
 def test_every_mode_matches_the_reference_files(selftest, tmp_path):
-    names = golden_files()
+    names = [f for f in golden_files() if not f.startswith("serial.")]
     assert len(names) == 20  # 2 modes x 2 x 2 shared files + 3 ranks x 2 x 2 per-rank files
     run(selftest, 3, tmp_path)
     for f in names:
@@ -68,3 +68,45 @@ def test_against_the_reference_class_itself(selftest, tmp_path, nranks):
         assert filecmp.cmp(ref_dir / f, mine_dir / f, shallow=False), f
         if nranks == 3:  # the committed copies are current
             assert filecmp.cmp(ref_dir / f, os.path.join(GOLD, f), shallow=False), f
+
+
+def _serial_frames():
+    """the frames host/slab_traj_selftest.cpp hands to the serial Logging class (traj_cases.hpp: ranks 0, 2, 0)"""
+    import numpy as np
+
+    def frame_xy(rank, frame):
+        n = (0 if rank == 1 else 2 * rank + 3) + frame
+        xy = []
+        for i in range(n):
+            x = 0.123456789012345678 + 1.7320508075688772 * i + 3.0 * rank + 0.001 * frame
+            y = 12.345678901234567 / (1.0 + i + rank) + 1e-7 * frame
+            if i == 1:
+                x = 1.0e-9 * (rank + 1)
+            if i == 2:
+                y = 12.0
+            xy.append((x, y))
+        return np.array(xy, dtype=np.float64).reshape(-1, 2)
+
+    return [frame_xy(0, 0), frame_xy(2, 1), frame_xy(0, 2)], [0, 100, 200]
+
+
+def test_serial_position_logs(selftest, tmp_path):
+    """Logging::logPositions_xyz / logPositions_dump of the serial shim (host/mc2d_host.cpp) against the reference's
+    (serial_src/logging.cpp:30-79): byte for byte with the committed files and, when oracle/_ref is built, with the
+    unmodified reference class fed the same doubles."""
+    run(selftest, 3, tmp_path)
+    for f in ("serial.xyz", "serial.dump"):
+        assert filecmp.cmp(os.path.join(GOLD, f), tmp_path / f, shallow=False), f
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+
+    if not ol.have_ref() or not hasattr(ol.Ref().lib, "ref_log_positions"):
+        pytest.skip("oracle/_ref/libmc2d_ref.so not built with ref_log_positions")
+    frames, ts = _serial_frames()
+    ref = ol.Ref()
+    ref.log_positions(tmp_path / "ref.xyz", tmp_path / "ref_xyz.dat", False, 20.0, 12.345678901234567, frames, ts)
+    ref.log_positions(tmp_path / "ref.dump", tmp_path / "ref_dump.dat", True, 20.0, 12.345678901234567, frames, ts)
+    assert filecmp.cmp(tmp_path / "ref.xyz", tmp_path / "serial.xyz", shallow=False)
+    assert filecmp.cmp(tmp_path / "ref.dump", tmp_path / "serial.dump", shallow=False)
